@@ -1,0 +1,444 @@
+"""Host side of the B200 denoising path: weight folding, batch packing, buffer ownership and kernel sequencing.
+
+PyTorch is used only for device memory, streams and one-off setup gathers; every per-step computation is a
+hand-written sm_100a kernel reached through the C ABI (include/diffphore_b200.h).  The sequence mirrors
+    TensorProductScoreModel.forward         /root/reference/src/models/score_model_phore.py:294-378
+    LigPhoreEncoder.forward                 /root/reference/src/models/score_model_phore.py:644-712
+    sampling_phore (one step)               /root/reference/src/utils/sampling.py:204-255
+"""
+import math
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import lib as L
+from .irreps import IRREP_SEQ, parse_irreps, irreps_dim, sh_irreps, fctp_instructions, full_tp_irreps_out
+
+DEFAULT_CONFIG = dict(ns=20, nv=10, num_conv_layers=4, sigma_embed_dim=20, distance_embed_dim=20,
+                      cross_distance_embed_dim=20, lig_max_radius=5.0, cross_max_distance=25.0,
+                      center_max_distance=30.0, embedding_scale=10000, scaler=100.0,
+                      clash_cutoff=[1.0, 2.0, 3.0, 4.0, 5.0], max_neighbors=32,
+                      tr_sigma_min=0.1, tr_sigma_max=5.0, rot_sigma_min=0.1, rot_sigma_max=1.5,
+                      tor_sigma_min=0.0314, tor_sigma_max=3.14, no_clamp=False)
+
+LAYER_DIMS = [20, 50, 80, 100, 100]
+
+
+def _f32(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+def sinusoidal_embedding(t, dim=20, scale=10000.0, max_positions=10000):
+    """get_timestep_embedding('sinusoidal') of diffusion_utils.py:82-132 for one scalar t (fp32 like the reference)."""
+    half = dim // 2
+    freq = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(max_positions) / (half - 1)))
+    x = (torch.tensor([scale], dtype=torch.float32) * torch.tensor([t], dtype=torch.float32)).float()[:, None] * freq[None, :]
+    return torch.cat([torch.sin(x), torch.cos(x)], dim=1)[0]
+
+
+class ConvWeights:
+    """One TensorProductConvLayer (smp:76-149) prepared for dp_edge_mlp / dp_tp_scatter."""
+
+    def __init__(self, sd, prefix, layer_id, in_irreps, sh_ir, out_irreps, device):
+        instrs, numel = fctp_instructions(in_irreps, sh_ir, out_irreps)
+        w3 = sd[prefix + '.fc.3.weight']
+        if w3.shape[0] != numel:
+            raise ValueError(f'{prefix}: fc.3 has {w3.shape[0]} rows, instruction table needs {numel}')
+        self.layer_id, self.W = layer_id, numel
+        self.in_dim, self.hid = sd[prefix + '.fc.0.weight'].shape[1], sd[prefix + '.fc.0.weight'].shape[0]
+        self.w1 = _f32(sd[prefix + '.fc.0.weight']).to(device)
+        self.b1 = _f32(sd[prefix + '.fc.0.bias']).to(device)
+        self.w2t = torch.cat([_f32(w3).T, _f32(sd[prefix + '.fc.3.bias'])[None, :]], 0).contiguous().to(device)
+        # eval BatchNorm (e3nn.nn.BatchNorm) and path weights folded into per-component scale/shift
+        bw, bb = sd[prefix + '.batch_norm.weight'].double(), sd[prefix + '.batch_norm.bias'].double()
+        rm, rv = sd[prefix + '.batch_norm.running_mean'].double(), sd[prefix + '.batch_norm.running_var'].double()
+        fan = {}
+        for ins in instrs:
+            fan[ins.io] = fan.get(ins.io, 0) + in_irreps[ins.i1][0]
+        scale, shift, iw, ib = [], [], 0, 0
+        for io, (mul, l, p) in enumerate(out_irreps):
+            pw = math.sqrt((2 * l + 1) / fan[io]) if io in fan else 0.0
+            s = bw[iw:iw + mul] / torch.sqrt(rv[iw:iw + mul] + 1e-5)
+            if l == 0 and p == 1:
+                sh = bb[ib:ib + mul] - rm[ib:ib + mul] * s
+                ib += mul
+            else:
+                sh = torch.zeros(mul, dtype=torch.float64)
+            scale.append((s * pw).repeat_interleave(2 * l + 1))
+            shift.append(sh.repeat_interleave(2 * l + 1))
+            iw += mul
+        self.oscale = torch.cat(scale).float().contiguous().to(device)
+        self.oshift = torch.cat(shift).float().contiguous().to(device)
+        self.d_in, self.d_out = irreps_dim(in_irreps), irreps_dim(out_irreps)
+
+
+class ModelWeights:
+    """Everything the kernels need from a reference-format state_dict (checkpoint loads unchanged)."""
+
+    def __init__(self, state_dict, device, config=None):
+        self.cfg = dict(DEFAULT_CONFIG)
+        if config:
+            self.cfg.update(config)
+        self.device = device
+        sd = state_dict
+        self.lib = L.load()
+        ns, nv = self.cfg['ns'], self.cfg['nv']
+        if (ns, nv, self.cfg['num_conv_layers']) != (20, 10, 4):
+            raise NotImplementedError('kernels are specialised for ns=20, nv=10, num_conv_layers=4 (shipped config)')
+        seq = [parse_irreps(s) for s in IRREP_SEQ(ns, nv)]
+        sh = sh_irreps(2)
+        sh45, _ = full_tp_irreps_out(sh, [(1, 2, 1)])
+        self.convs = {}
+        for l in range(4):
+            for fam in ('lig', 'phore', 'lig_to_phore', 'phore_to_lig', 'lig_to_phore_norm', 'phore_to_lig_norm'):
+                if l == 3 and fam in ('phore', 'lig_to_phore', 'lig_to_phore_norm'):
+                    continue                                            # never executed (smp:691)
+                self.convs[(fam, l)] = ConvWeights(sd, f'encoder.{fam}_conv_layers.{l}', l, seq[min(l, 3)], sh,
+                                                   seq[min(l + 1, 3)], device)
+        self.convs['final'] = ConvWeights(sd, 'final_conv', L.TP_FINAL, seq[3], sh, parse_irreps('2x1o + 2x1e'), device)
+        self.convs['tor'] = ConvWeights(sd, 'tor_bond_conv', L.TP_TOR, seq[3], sh45, parse_irreps(f'{ns}x0o + {ns}x0e'),
+                                        device)
+        # small weights
+        self._keep = []
+
+        def dev(t):
+            t = _f32(t).to(device)
+            self._keep.append(t)
+            return t.data_ptr()
+
+        def mlp(prefix, bias=True):
+            return L.DpMlp(dev(sd[prefix + '.0.weight']), dev(sd[prefix + '.0.bias']) if bias else None,
+                           dev(sd[prefix + '.3.weight']), dev(sd[prefix + '.3.bias']) if bias else None)
+
+        sw = L.DpSmallWeights()
+        sw.lig_edge, sw.pp_edge = mlp('encoder.lig_edge_embedding'), mlp('encoder.phore_edge_embedding')
+        sw.cross_edge = mlp('encoder.cross_edge_embedding')
+        sw.cdt, sw.pdt = mlp('encoder.cross_distance_transition'), mlp('encoder.phore_direction_transition')
+        sw.pmt = mlp('encoder.phoretype_match_transition')
+        sw.center_edge, sw.final_edge = mlp('center_edge_embedding'), mlp('final_edge_embedding')
+        sw.tr_final, sw.rot_final = mlp('tr_final_layer'), mlp('rot_final_layer')
+        sw.boarder_tables = dev(torch.stack([sd[f'encoder.boarder_embedding.atom_embedding_list.{i}.weight'] for i in range(5)]))
+        sw.boarder_w = dev(sd['encoder.boarder_embedding.linear.weight'][:, 0])
+        sw.boarder_b = dev(sd['encoder.boarder_embedding.linear.bias'])
+        sw.tor_w0 = dev(sd['tor_final_layer.0.weight'])
+        sw.tor_w3 = dev(sd['tor_final_layer.3.weight'][0])
+        self.sw = sw
+        # host copies for the per-step folds and the static embeddings
+        self.h = {k: _f32(v).cpu() for k, v in sd.items() if v.dim() <= 2 and v.numel() < 10000}
+        self.lig_tables = [_f32(sd[f'encoder.lig_node_embedding.atom_embedding_list.{i}.weight']).to(device) for i in range(16)]
+        self.ph_tables = [_f32(sd[f'encoder.phore_node_embedding.atom_embedding_list.{i}.weight']).to(device) for i in range(3)]
+        self.ph_lin_w = _f32(sd['encoder.phore_node_embedding.linear.weight']).to(device)
+        # constants
+        c = L.DpConstants()
+        for i, key in enumerate(['encoder.lig_distance_expansion.offset', 'encoder.phore_distance_expansion.offset',
+                                 'encoder.cross_distance_expansion.offset', 'center_distance_expansion.offset']):
+            off = _f32(sd[key]).cpu()
+            for k in range(20):
+                c.rbf_mu[i][k] = float(off[k])
+            c.rbf_coeff[i] = -0.5 / (off[1] - off[0]).item() ** 2           # smp:1010
+        for i, v in enumerate(self.cfg['clash_cutoff']):
+            c.clash_cutoff[i] = float(v)
+        c.lig_radius, c.scaler = float(self.cfg['lig_max_radius']), float(self.cfg['scaler'])
+        c.max_neighbors, c.no_clamp = int(self.cfg['max_neighbors']), int(bool(self.cfg['no_clamp']))
+        self.consts = c
+        L.check(self.lib.dp_set_constants(c), 'dp_set_constants')
+
+    # ------------------------------------------------------------------ per-noise-level constant block
+    def t_to_sigma(self, t):
+        """diffusion_utils.py:16-20, evaluated in fp32 like the reference's tensor path (complex_t is fp32)."""
+        c = self.cfg
+        tt = torch.tensor(t, dtype=torch.float32)
+        return tuple(float((c[f'{k}_sigma_min'] ** (1 - tt) * c[f'{k}_sigma_max'] ** tt).item()) for k in ('tr', 'rot', 'tor'))
+
+    def step_consts(self, t, so3_norm, torus_norm, dt=None):
+        """256-float block for noise level t.  so3_norm / torus_norm: callables sigma(np.float32 array) -> array
+        (utils/so3.py:92-96, utils/torus.py:82-86).  dt: Euler–Maruyama step (None -> score model only)."""
+        c, h = self.cfg, self.h
+        semb = sinusoidal_embedding(float(t), c['sigma_embed_dim'], c['embedding_scale'])
+        out = torch.zeros(L.SC['SIZE'], dtype=torch.float32)
+        out[0:20] = semb
+
+        def fold(wkey, bkey, lo, hi):
+            return h[wkey][:, lo:hi] @ semb + h[bkey]
+
+        out[20:40] = fold('encoder.lig_node_embedding.linear.weight', 'encoder.lig_node_embedding.linear.bias', 0, 20)
+        out[40:60] = fold('encoder.phore_node_embedding.linear.weight', 'encoder.phore_node_embedding.linear.bias', 2, 22)
+        out[60:80] = fold('encoder.lig_edge_embedding.0.weight', 'encoder.lig_edge_embedding.0.bias', 4, 24)
+        out[80:100] = fold('encoder.phore_edge_embedding.0.weight', 'encoder.phore_edge_embedding.0.bias', 0, 20)
+        out[100:120] = fold('encoder.cross_edge_embedding.0.weight', 'encoder.cross_edge_embedding.0.bias', 0, 20)
+        out[120:140] = fold('center_edge_embedding.0.weight', 'center_edge_embedding.0.bias', 20, 40)
+        out[140:160] = fold('tr_final_layer.0.weight', 'tr_final_layer.0.bias', 1, 21)
+        out[160:180] = fold('rot_final_layer.0.weight', 'rot_final_layer.0.bias', 1, 21)
+        tr_s, rot_s, tor_s = self.t_to_sigma(t)
+        out[180] = 1.0 / np.float32(tr_s)
+        out[181] = float(np.asarray(so3_norm(np.asarray([rot_s], dtype=np.float32)))[0])
+        out[182] = float(np.sqrt(np.float32(np.asarray(torus_norm(np.asarray([tor_s], dtype=np.float32)))[0])))
+        if dt is not None:
+            # sampling.py:223-246 — sigma from numpy float64 t, g in float64, cast to fp32 at the multiply
+            t64 = float(t)
+            trs = c['tr_sigma_min'] ** (1 - t64) * c['tr_sigma_max'] ** t64
+            rots = c['rot_sigma_min'] ** (1 - t64) * c['rot_sigma_max'] ** t64
+            tors = c['tor_sigma_min'] ** (1 - t64) * c['tor_sigma_max'] ** t64
+            tr_g = trs * math.sqrt(2 * math.log(c['tr_sigma_max'] / c['tr_sigma_min']))
+            rot_g = 2 * rots * math.sqrt(math.log(c['rot_sigma_max'] / c['rot_sigma_min']))
+            tor_g = tors * math.sqrt(2 * math.log(c['tor_sigma_max'] / c['tor_sigma_min']))
+            out[183], out[184] = tr_g ** 2 * dt, tr_g * math.sqrt(dt)
+            out[185], out[186] = rot_g ** 2 * dt, rot_g * math.sqrt(dt)
+            out[187], out[188] = tor_g ** 2 * dt, tor_g * math.sqrt(dt)
+        return out
+
+
+# =====================================================================================================================
+# batch packing
+# =====================================================================================================================
+def _pair_arrays(g):
+    """numpy view of one HeteroGraph / PyG HeteroData pair in the kernels' layout (local indices)."""
+    lig, ph = g['ligand'], g['phore']
+    n = lig.pos.shape[0]
+    ei = g['ligand', 'ligand'].edge_index.cpu().numpy().astype(np.int64)
+    ea = g['ligand', 'ligand'].edge_attr.cpu().numpy()
+    btype = ea.argmax(1).astype(np.int32) if ea.size else np.zeros(0, np.int32)
+    mask = lig.edge_mask.cpu().numpy().astype(bool)
+    order = np.argsort(ei[0], kind='stable')
+    bond_ptr = np.zeros(n + 1, np.int32)
+    np.add.at(bond_ptr, ei[0] + 1, 1)
+    bond_ptr = np.cumsum(bond_ptr).astype(np.int32)
+    mr = lig.mask_rotate
+    mr = np.asarray(mr if isinstance(mr, np.ndarray) else mr[0]).astype(np.uint8).reshape(int(mask.sum()), n)
+    pe = g['phore', 'phore'].edge_index.cpu().numpy().astype(np.int64)
+    po = np.argsort(pe[0], kind='stable')
+    P = ph.pos.shape[0]
+    pp_ptr = np.zeros(P + 1, np.int32)
+    np.add.at(pp_ptr, pe[0] + 1, 1)
+    return SimpleNamespace(
+        n=n, P=P, x=lig.x.cpu().numpy().astype(np.int64), pos=lig.pos.cpu().numpy().astype(np.float32),
+        norm=lig.norm.cpu().numpy().astype(np.float32).reshape(n, 33), phorefp=lig.phorefp.cpu().numpy().astype(np.float32),
+        na1=lig.norm_angle1.cpu().numpy().astype(np.float32), na2=lig.norm_angle2.cpu().numpy().astype(np.float32),
+        bond_ptr=bond_ptr, bond_dst=ei[1][order].astype(np.int32), bond_type=btype[order],
+        rot_u=ei[0][mask].astype(np.int32), rot_v=ei[1][mask].astype(np.int32), mask=mr,
+        px=ph.x.cpu().numpy().astype(np.float32), ppos=ph.pos.cpu().numpy().astype(np.float32),
+        pnorm=ph.norm.cpu().numpy().astype(np.float32), ptype=ph.phoretype.cpu().numpy().astype(np.float32),
+        pp_src=pe[0][po].astype(np.int32), pp_dst=pe[1][po].astype(np.int32), pp_ptr=np.cumsum(pp_ptr).astype(np.int32))
+
+
+class PackedBatch:
+    """Flattened device arrays for B graphs (PyG-Batch-like; graph g = pair g // samples, sample g % samples)."""
+
+    def __init__(self, graphs, samples_per_graph, weights, device):
+        S = samples_per_graph
+        pa = [_pair_arrays(g) for g in graphs]
+        B = len(pa) * S
+        self.B, self.S, self.device = B, S, device
+        rep = lambda arrs: np.concatenate([np.tile(a, (S,) + (1,) * (a.ndim - 1)) for a in arrs], 0)
+        n_per = np.repeat([p.n for p in pa], S)
+        P_per = np.repeat([p.P for p in pa], S)
+        nrot_per = np.repeat([len(p.rot_u) for p in pa], S)
+        lig_ptr = np.concatenate([[0], np.cumsum(n_per)]).astype(np.int64)
+        ph_ptr = np.concatenate([[0], np.cumsum(P_per)]).astype(np.int64)
+        rot_ptr = np.concatenate([[0], np.cumsum(nrot_per)]).astype(np.int64)
+        self.n_lig, self.n_ph, self.n_rot = int(lig_ptr[-1]), int(ph_ptr[-1]), int(rot_ptr[-1])
+        self.max_atoms, self.max_rot = int(n_per.max()), int(nrot_per.max())
+        self.n_per, self.P_per, self.nrot_per = n_per, P_per, nrot_per
+        gi = 0
+        bond_ptr, bond_dst, bond_type, rot_u, rot_v, pp_src, pp_dst, pp_ptr = [], [], [], [], [], [], [], []
+        cl, cp, cptr, masks, moff = [], [], [0], [], [0]
+        cl_t, cp_t, perm_t, cseg_ph = [], [], [], [0]
+        e_off = pp_off = c_off = 0
+        for p in pa:
+            for s in range(S):
+                a0, p0 = int(lig_ptr[gi]), int(ph_ptr[gi])
+                bond_ptr.append(p.bond_ptr[:-1] + e_off)
+                bond_dst.append(p.bond_dst + a0)
+                bond_type.append(p.bond_type)
+                e_off += len(p.bond_dst)
+                rot_u.append(p.rot_u + a0)
+                rot_v.append(p.rot_v + a0)
+                pp_src.append(p.pp_src + p0)
+                pp_dst.append(p.pp_dst + p0)
+                pp_ptr.append(p.pp_ptr[:-1] + pp_off)
+                pp_off += len(p.pp_src)
+                # cross edges sorted by (lig, phore)  (smp:770-781)
+                a = np.repeat(np.arange(p.n), p.P)
+                q = np.tile(np.arange(p.P), p.n)
+                cl.append(a + a0)
+                cp.append(q + p0)
+                # transposed order (phore-major) for the lig->phore convolutions
+                qt = np.repeat(np.arange(p.P), p.n)
+                at = np.tile(np.arange(p.n), p.P)
+                cl_t.append(at + a0)
+                cp_t.append(qt + p0)
+                perm_t.append(c_off + at * p.P + qt)
+                c_off += p.n * p.P
+                cptr.append(c_off)
+                masks.append(p.mask.reshape(-1))
+                moff.append(moff[-1] + p.mask.size)
+                gi += 1
+        i32 = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.int32))).to(device)
+        f32 = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32))).to(device)
+        cat = lambda l, dt: np.concatenate(l).astype(dt) if len(l) else np.zeros(0, dt)
+        self.lig_ptr, self.ph_ptr, self.rot_ptr = i32(lig_ptr), i32(ph_ptr), i32(rot_ptr)
+        self.lig_batch = i32(np.repeat(np.arange(B), n_per))
+        self.bond_ptr = i32(np.concatenate([cat(bond_ptr, np.int64), [e_off]]))
+        self.bond_dst, self.bond_type = i32(cat(bond_dst, np.int64)), i32(cat(bond_type, np.int64))
+        self.n_bond = e_off
+        self.rot_u, self.rot_v = i32(cat(rot_u, np.int64)), i32(cat(rot_v, np.int64))
+        self.pp_src, self.pp_dst = i32(cat(pp_src, np.int64)), i32(cat(pp_dst, np.int64))
+        self.pp_ptr = i32(np.concatenate([cat(pp_ptr, np.int64), [pp_off]]))
+        self.n_pp = pp_off
+        self.cross_lig, self.cross_ph, self.cross_ptr = i32(cat(cl, np.int64)), i32(cat(cp, np.int64)), i32(cptr)
+        self.cross_lig_t, self.cross_ph_t, self.cross_perm_t = i32(cat(cl_t, np.int64)), i32(cat(cp_t, np.int64)), i32(cat(perm_t, np.int64))
+        self.n_cross = c_off
+        # CSR of cross edges by ligand atom (canonical order) and by phore node (transposed order)
+        self.cross_seg_lig = i32(np.concatenate([[0], np.cumsum(np.repeat(P_per, n_per))]))
+        self.cross_seg_ph = i32(np.concatenate([[0], np.cumsum(np.repeat(n_per, P_per))]))
+        self.mask = torch.from_numpy(cat(masks, np.uint8)).to(device)
+        self.mask_off = torch.from_numpy(np.asarray(moff[:-1], dtype=np.int64)).to(device)
+        self.lig_arange = torch.arange(self.n_lig, dtype=torch.int32, device=device)
+        # node-level tensors
+        self.pos = f32(rep([p.pos for p in pa]))
+        self.norm = f32(rep([p.norm for p in pa]))
+        self.phorefp, self.na1, self.na2 = f32(rep([p.phorefp for p in pa])), f32(rep([p.na1 for p in pa])), f32(rep([p.na2 for p in pa]))
+        self.ppos, self.pnorm, self.ptype = f32(rep([p.ppos for p in pa])), f32(rep([p.pnorm for p in pa])), f32(rep([p.ptype for p in pa]))
+        x = torch.from_numpy(rep([p.x for p in pa])).to(device)
+        px = f32(rep([p.px for p in pa]))
+        # static parts of the AtomEncoders (setup-time gathers; smp:64-73)
+        w = weights
+        ls = torch.zeros(self.n_lig, 20, device=device)
+        for i in range(16):
+            ls = ls + w.lig_tables[i][x[:, i]]
+        ps = torch.zeros(self.n_ph, 20, device=device)
+        for i in range(3):
+            ps = ps + w.ph_tables[i][px[:, i].long()]
+        ps = ps + px[:, 3:5] @ w.ph_lin_w[:, 0:2].T
+        self.lig_static, self.ph_static = ls.contiguous(), ps.contiguous()
+        # capacities of the dynamic edge sets
+        k = weights.cfg['max_neighbors']
+        self.ll_cap = int(e_off + np.sum(n_per * np.minimum(n_per - 1, k + 1)))
+        self.tor_cap = int(np.sum(nrot_per * np.minimum(n_per, k)))
+
+
+class Workspace:
+    """All per-step device buffers for one PackedBatch."""
+
+    def __init__(self, b, weights):
+        dev = b.device
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        i = lambda *s: torch.empty(*s, dtype=torch.int32, device=dev)
+        self.lig_h = [f(b.n_lig, d) for d in LAYER_DIMS]
+        self.ph_h = [f(b.n_ph, d) for d in LAYER_DIMS[:4]]
+        self.thr, self.deg, self.gcount, self.gstart = i(b.n_lig), i(max(b.n_lig, b.n_rot, 1)), i(b.B), i(b.B + 1)
+        self.ll_ptr, self.ll_src, self.ll_dst = i(b.n_lig + 1), i(b.ll_cap), i(b.ll_cap)
+        self.ll_emb, self.ll_sh, self.ll_n = f(b.ll_cap, 20), f(b.ll_cap, 9), i(1)
+        self.pp_h, self.pp_sh, self.pp_emb = f(b.n_pp, 20), f(b.n_pp, 9), f(b.n_pp, 20)
+        self.cross_h, self.cross_fm, self.cross_tw = f(b.n_cross, 20), f(b.n_cross), f(b.n_cross)
+        self.cross_emb, self.cross_sh, self.cross_nsh = f(b.n_cross, 20), f(b.n_cross, 9), f(b.n_cross, 9)
+        self.c_emb, self.c_sh, self.gpred = f(b.n_lig, 20), f(b.n_lig, 9), f(b.B, 12)
+        self.t_ptr, self.t_atom, self.t_u, self.t_v = i(b.n_rot + 1), i(max(b.tor_cap, 1)), i(max(b.tor_cap, 1)), i(max(b.tor_cap, 1))
+        self.t_emb, self.t_sh, self.t_n = f(max(b.tor_cap, 1), 20), f(max(b.tor_cap, 1), 8), i(1)
+        self.tor_feat = f(max(b.n_rot, 1), 40)
+        self.tr, self.rot, self.tor = f(b.B, 3), f(b.B, 3), f(max(b.n_rot, 1))
+        w_elems = max(b.ll_cap * 2200, b.n_cross * 2200, b.n_pp * 1600, b.tor_cap * 1600, b.n_lig * 200, 1)
+        self.wbuf = f(w_elems)
+        self.n_launches = 0
+
+
+class Engine:
+    """Runs the score model and the conformer update for one PackedBatch on the current CUDA stream."""
+
+    def __init__(self, weights):
+        self.w = weights
+        self.lib = weights.lib
+
+    def pack(self, graphs, samples_per_graph=1):
+        b = PackedBatch(graphs, samples_per_graph, self.w, self.w.device)
+        ws = Workspace(b, self.w)
+        st = torch.cuda.current_stream().cuda_stream
+        sw = self.w.sw
+        L.check(self.lib.dp_pp_setup(L.ptr(b.ppos), L.ptr(b.pp_src), L.ptr(b.pp_dst), b.n_pp, sw, L.ptr(ws.pp_h),
+                                     L.ptr(ws.pp_sh), st), 'dp_pp_setup')
+        L.check(self.lib.dp_cross_setup(L.ptr(b.cross_lig), L.ptr(b.cross_ph), b.n_cross, L.ptr(b.phorefp), L.ptr(b.ptype),
+                                        sw, L.ptr(ws.cross_h), L.ptr(ws.cross_fm), st), 'dp_cross_setup')
+        return b, ws
+
+    # ------------------------------------------------------------------ one TensorProductConvLayer
+    def _conv(self, cw, ws, emb, perm, tb, idxB, tc, idxC, idxC2, n_dev, n_cap, node_in, gather, sh, sh_stride, seg, out,
+              residual, res_dim, mode, n_out, st):
+        p = L.ptr
+        L.check(self.lib.dp_edge_mlp(p(emb), p(perm), p(tb), p(idxB), tb.shape[1], p(tc), p(idxC), p(idxC2),
+                                     tc.shape[1] if tc is not None else 0, p(cw.w1), p(cw.b1), p(cw.w2t), cw.in_dim, cw.hid,
+                                     cw.W, p(n_dev), n_cap, p(ws.wbuf), st), 'dp_edge_mlp')
+        L.check(self.lib.dp_tp_scatter(cw.layer_id, p(node_in), p(gather), p(perm), p(sh), sh_stride, p(ws.wbuf), p(seg),
+                                       p(cw.oscale), p(cw.oshift), p(out), p(residual), res_dim, mode, n_out, st),
+                'dp_tp_scatter')
+        ws.n_launches += 2
+
+    def forward(self, b, ws, sc):
+        """Score model for the batch's current pose.  sc: device tensor [256] (ModelWeights.step_consts).
+        Results land in ws.tr [B,3], ws.rot [B,3], ws.tor [n_rot]."""
+        lib, sw, p = self.lib, self.w.sw, L.ptr
+        st = torch.cuda.current_stream().cuda_stream
+        scp = p(sc)
+        L.check(lib.dp_node_embed(p(b.pos), p(b.ppos), p(b.lig_batch), p(b.ph_ptr), p(b.ptype), p(b.lig_static),
+                                  p(b.ph_static), b.n_lig, b.n_ph, sw, scp, p(ws.lig_h[0]), p(ws.ph_h[0]), st), 'dp_node_embed')
+        L.check(lib.dp_lig_graph(p(b.pos), p(b.lig_ptr), p(b.bond_ptr), p(b.bond_dst), p(b.bond_type), b.B, b.n_lig,
+                                 b.max_atoms, sw, scp, p(ws.thr), p(ws.deg), p(ws.gcount), p(ws.gstart), p(ws.ll_ptr),
+                                 p(ws.ll_src), p(ws.ll_dst), p(ws.ll_emb), p(ws.ll_sh), p(ws.ll_n), st), 'dp_lig_graph')
+        L.check(lib.dp_pp_step(p(ws.pp_h), b.n_pp, sw, scp, p(ws.pp_emb), st), 'dp_pp_step')
+        L.check(lib.dp_cross_step(p(b.pos), p(b.norm), p(b.ppos), p(b.pnorm), p(b.lig_ptr), p(b.ph_ptr), p(b.cross_ptr),
+                                  b.B, b.max_atoms, p(b.phorefp), p(b.ptype), p(b.na1), p(b.na2), p(ws.cross_h),
+                                  p(ws.cross_fm), sw, scp, p(ws.cross_tw), p(ws.cross_emb), p(ws.cross_sh),
+                                  p(ws.cross_nsh), st), 'dp_cross_step')
+        ws.n_launches += 6
+        cv = self.w.convs
+        for l in range(4):
+            lh, ph, lo = ws.lig_h[l], ws.ph_h[l] if l < 4 else None, ws.lig_h[l + 1]
+            d = LAYER_DIMS[l]
+            self._conv(cv[('lig', l)], ws, ws.ll_emb, None, lh, ws.ll_src, lh, ws.ll_dst, None, ws.ll_n, b.ll_cap,
+                       lh, ws.ll_dst, ws.ll_sh, 9, ws.ll_ptr, lo, lh, d, 1, b.n_lig, st)
+            self._conv(cv[('phore_to_lig', l)], ws, ws.cross_emb, None, lh, b.cross_lig, ph, b.cross_ph, None, None,
+                       b.n_cross, ph, b.cross_ph, ws.cross_sh, 9, b.cross_seg_lig, lo, None, 0, 2, b.n_lig, st)
+            self._conv(cv[('phore_to_lig_norm', l)], ws, ws.cross_emb, None, lh, b.cross_lig, ph, b.cross_ph, None, None,
+                       b.n_cross, ph, b.cross_ph, ws.cross_nsh, 9, b.cross_seg_lig, lo, None, 0, 2, b.n_lig, st)
+            if l != 3:
+                po = ws.ph_h[l + 1]
+                self._conv(cv[('phore', l)], ws, ws.pp_emb, None, ph, b.pp_src, ph, b.pp_dst, None, None, b.n_pp,
+                           ph, b.pp_dst, ws.pp_sh, 9, b.pp_ptr, po, ph, d, 1, b.n_ph, st)
+                self._conv(cv[('lig_to_phore', l)], ws, ws.cross_emb, b.cross_perm_t, lh, b.cross_lig_t, ph, b.cross_ph_t,
+                           None, None, b.n_cross, lh, b.cross_lig_t, ws.cross_sh, 9, b.cross_seg_ph, po, None, 0, 2,
+                           b.n_ph, st)
+                self._conv(cv[('lig_to_phore_norm', l)], ws, ws.cross_emb, b.cross_perm_t, lh, b.cross_lig_t, ph,
+                           b.cross_ph_t, None, None, b.n_cross, lh, b.cross_lig_t, ws.cross_nsh, 9, b.cross_seg_ph, po,
+                           None, 0, 2, b.n_ph, st)
+        h4 = ws.lig_h[4]
+        L.check(lib.dp_center_step(p(b.pos), p(b.lig_ptr), b.B, sw, scp, p(ws.c_emb), p(ws.c_sh), st), 'dp_center_step')
+        self._conv(cv['final'], ws, ws.c_emb, None, h4, b.lig_arange, None, None, None, None, b.n_lig, h4, None, ws.c_sh, 9,
+                   b.lig_ptr, ws.gpred, None, 0, 0, b.B, st)
+        L.check(lib.dp_score_head(p(ws.gpred), b.B, sw, scp, p(ws.tr), p(ws.rot), st), 'dp_score_head')
+        ws.n_launches += 2
+        if b.n_rot > 0:
+            L.check(lib.dp_tor_graph(p(b.pos), p(b.lig_ptr), p(b.rot_ptr), p(b.rot_u), p(b.rot_v), b.B, b.n_rot, sw,
+                                     p(ws.deg), p(ws.gcount), p(ws.gstart), p(ws.t_ptr), p(ws.t_atom), p(ws.t_u), p(ws.t_v),
+                                     p(ws.t_emb), p(ws.t_sh), p(ws.t_n), st), 'dp_tor_graph')
+            self._conv(cv['tor'], ws, ws.t_emb, None, h4, ws.t_atom, h4, ws.t_u, ws.t_v, ws.t_n, b.tor_cap, h4, ws.t_atom,
+                       ws.t_sh, 8, ws.t_ptr, ws.tor_feat, None, 0, 0, b.n_rot, st)
+            L.check(lib.dp_tor_head(p(ws.tor_feat), b.n_rot, sw, scp, p(ws.tor), st), 'dp_tor_head')
+            ws.n_launches += 4
+        return ws.tr, ws.rot, ws.tor[:b.n_rot]
+
+    def update(self, b, ws, sc, tr_z=None, rot_z=None, tor_z=None, no_torsion=False):
+        """Apply the Euler–Maruyama step (sampling.py:223-254) to b.pos / b.norm in place."""
+        p = L.ptr
+        st = torch.cuda.current_stream().cuda_stream
+        L.check(self.lib.dp_conformer_update(p(b.pos), p(b.norm), p(b.lig_ptr), p(b.rot_ptr), p(b.rot_u), p(b.rot_v),
+                                             p(b.mask), p(b.mask_off), b.B, b.max_atoms, b.max_rot, p(ws.tr), p(ws.rot),
+                                             p(ws.tor), p(tr_z), p(rot_z), p(tor_z), p(sc), int(no_torsion), st),
+                'dp_conformer_update')
+        ws.n_launches += 1
+
+    def randomize(self, b, tor_init, rot_init, tr_init, no_torsion=False):
+        p = L.ptr
+        st = torch.cuda.current_stream().cuda_stream
+        L.check(self.lib.dp_randomize_position(p(b.pos), p(b.norm), p(b.lig_ptr), p(b.rot_ptr), p(b.rot_u), p(b.rot_v),
+                                               p(b.mask), p(b.mask_off), b.B, b.max_atoms, b.max_rot, p(tor_init),
+                                               p(rot_init), p(tr_init), int(no_torsion), st), 'dp_randomize_position')
