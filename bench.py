@@ -1,0 +1,240 @@
+#!/usr/bin/env python
+"""Benchmark of the DiffPhore denoising hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
+
+One bench "step" = one full reverse-diffusion pass (20 denoising steps: score model + conformer update) over the
+BASELINE.json configs[1] workload: 256 synthetic ligand–pharmacophore pairs (32 atoms / 8 pharmacophore points)
+x 40 samples per pair = 10 240 poses per GPU.  metric = denoised samples/s.
+
+  value : device-timed (CUDA events), graphs already packed and resident in HBM when the timed region starts
+  e2e   : the same work through the public API (DenoisingSampler.run on host graphs): host packing, H2D of the
+          packed batch, 20 steps, D2H of the final poses, all inside the timed region
+  --impl reference : the oracle (CPU restatement of the reference's op graph) on the host cores, bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'src'))
+
+N_PAIRS, N_ATOMS, N_PHORE, SAMPLES, INF_STEPS = 256, 32, 8, 40, 20
+WORKLOAD = 'synthetic 256 pairs (32 atoms / 8 phore points) x 40 samples x 20 denoising steps per GPU'
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        return float(p['hbm_gbs']), 'measured'
+    except Exception:
+        return 6650.0, 'fallback'
+
+
+class ClockSampler:
+    FIELDS = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits',
+                                          '-lms', '200', '-i', str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_reference_rate(n_pairs, samples, threads, steps=INF_STEPS):
+    """Oracle = reference op graph on CPU (materialised per-edge TP weights, index_add scatter, per-step re-collation,
+    per-sample scipy/LAPACK conformer update), batch_size = samples like the reference batches within a pair."""
+    from tests.parity_util import random_state_dict, load_pairs, make_draws, oracle_initial_graphs
+    from diffphore_b200.graph import collate
+    from oracle.model import OracleScoreModel, default_config
+    from oracle import sampler as osamp
+    from oracle.tables import So3ScoreNorm, TorusScoreNorm
+    torch.set_num_threads(threads)
+    sd = random_state_dict(0)
+    graphs = load_pairs('synthetic', n_pairs, N_ATOMS, N_PHORE)
+    init, noise, n_rot = make_draws(graphs, samples, 0, steps=steps)
+    dl = oracle_initial_graphs(graphs, samples, init, n_rot)
+    so3n, torn = So3ScoreNorm(), TorusScoreNorm()
+    om = OracleScoreModel(sd, so3n, torn)
+    for t in osamp.get_t_schedule(steps):                       # table rows are a one-off import cost in the reference
+        s = np.asarray([0.1 ** (1 - t) * 1.5 ** t], dtype=np.float32)
+        so3n(s)
+        torn(np.asarray([0.0314 ** (1 - t) * 3.14 ** t], dtype=np.float32))
+    t0 = time.time()
+    osamp.sampling(dl, om, steps, default_config(), collate, batch_size=samples, noise=noise)
+    dt = time.time() - t0
+    return len(dl) / dt, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--pairs', type=int, default=N_PAIRS)
+    ap.add_argument('--samples', type=int, default=SAMPLES)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    cores = os.cpu_count()
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        vals = []
+        n_pairs, samples = 1, 8
+        for _ in range(args.warmup if args.warmup < 2 else 1):
+            cpu_reference_rate(1, 2, cores, steps=2)
+        t0 = time.time()
+        for _ in range(args.steps):
+            r, dt = cpu_reference_rate(n_pairs, samples, cores)
+            vals.append(r)
+        v = float(np.mean(vals))
+        sample = f'{n_pairs} pair x {samples} samples x {INF_STEPS} steps of the cfg2 shape per bench step (oracle port of the reference CPU path)'
+        print(json.dumps({'metric': 'denoised samples/sec (20-step)', 'value': v, 'unit': 'samples/s', 'n_gpus': args.gpus,
+                          'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000 * (time.time() - t0) / args.steps,
+                          'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                          'data': 'synthetic graphs, random-init weights of the shipped architecture',
+                          'impl': 'reference', 'config': {'workload': WORKLOAD},
+                          'cpu_baseline': {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+                          'e2e': {'value': v, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        return
+
+    import torch.distributed as dist
+    from diffphore_b200.engine import ModelWeights
+    from diffphore_b200.sampler import DenoisingSampler
+    from diffphore_b200.synthetic import make_pairs
+    from diffphore_b200 import profiling
+    from tests.parity_util import random_state_dict
+    import __graft_entry__ as ge
+    ge.build()
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    sd = random_state_dict(0)
+    w = ModelWeights(sd, dev)
+    sampler = DenoisingSampler(w, INF_STEPS)
+    graphs = make_pairs(args.pairs, N_ATOMS, N_PHORE, first=rank * args.pairs)
+    n_samples_local = args.pairs * args.samples
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather_poses(pos_dev):
+        if world > 1:
+            out = [torch.empty_like(pos_dev) for _ in range(world)]
+            dist.all_gather(out, pos_dev)                       # the single NCCL collective of the path
+            return out
+        return [pos_dev]
+
+    # ---- device-resident arm: pack once per bench step outside the timed region
+    resident = sampler.prepare(graphs, args.samples)
+    for _ in range(args.warmup):
+        sampler.reset(resident, generator=gen)
+        sampler.run_resident(resident, generator=gen)
+        gather_poses(resident[-1][0].pos)
+    barrier()
+    prof = profiling.KernelTimer()
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = sampler.gpu_launches
+    times = []
+    for _ in range(args.steps):
+        sampler.reset(resident, generator=gen)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sampler.run_resident(resident, generator=gen, timer=prof)
+        gather_poses(resident[-1][0].pos)
+        e1.record()
+        barrier()
+        times.append(e0.elapsed_time(e1))
+    clk = clocks.stop()
+    launches = (sampler.gpu_launches - l0) // max(args.steps, 1)
+    ms = float(np.mean(times))
+    tmax = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    value = n_samples_local * world / (ms / 1000.0)
+    roof = prof.roofline(*peaks())
+
+    # ---- end-to-end arm through the public API with host inputs
+    e2e = None
+    if not args.no_e2e:
+        sampler.run(graphs[:8], args.samples, generator=gen)          # warm caches of the API path
+        barrier()
+        t_e2e = []
+        for _ in range(max(1, min(args.steps, 2))):
+            barrier()
+            t0 = time.perf_counter()
+            pos, ptr = sampler.run(graphs, args.samples, generator=gen, pinned=True)
+            gather_poses(pos.to(dev, non_blocking=True)) if world > 1 else None
+            barrier()
+            t_e2e.append(time.perf_counter() - t0)
+        te = torch.tensor([float(np.mean(t_e2e))], device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {'value': n_samples_local * world / float(te.item()), 'unit': 'samples/s',
+               'h2d_bytes_per_step': int(sampler.last_h2d_bytes), 'd2h_bytes_per_step': int(pos.numel() * 4)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r, dt = cpu_reference_rate(1, 8, cores)
+        cpu = {'value': r, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+               'sample': f'1 pair x 8 samples x {INF_STEPS} steps of the cfg2 shape ({dt:.1f} s of CPU work, oracle port)'}
+    if rank == 0:
+        print(json.dumps({'metric': 'denoised samples/sec (20-step)', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
+                          'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+                          'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                          'data': 'synthetic graphs (diffphore_b200/synthetic.py), random-init weights of the shipped architecture',
+                          'config': {'workload': WORKLOAD, 'pairs_per_gpu': args.pairs, 'samples_per_pair': args.samples,
+                                     'denoising_steps': INF_STEPS, 'l2': 'inputs larger than L2 (multi-GB per-edge weight stream)',
+                                     'parallelism': f'pairs sharded over {world} rank(s), one all_gather of poses'},
+                          'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof,
+                          'kernels': prof.summary(), 'cpu_baseline': cpu}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -80,7 +80,7 @@ class ModelWeights:
         self.cfg = dict(DEFAULT_CONFIG)
         if config:
             self.cfg.update(config)
-        self.device = device
+        self.device = device = torch.device(device)
         sd = state_dict
         self.lib = L.load()
         ns, nv = self.cfg['ns'], self.cfg['nv']
@@ -142,7 +142,8 @@ class ModelWeights:
         c.lig_radius, c.scaler = float(self.cfg['lig_max_radius']), float(self.cfg['scaler'])
         c.max_neighbors, c.no_clamp = int(self.cfg['max_neighbors']), int(bool(self.cfg['no_clamp']))
         self.consts = c
-        L.check(self.lib.dp_set_constants(c), 'dp_set_constants')
+        if device.type == 'cuda':           # host-only construction (CPU tests of the packing logic) skips the upload
+            L.check(self.lib.dp_set_constants(c), 'dp_set_constants')
 
     # ------------------------------------------------------------------ per-noise-level constant block
     def t_to_sigma(self, t):
@@ -171,7 +172,7 @@ class ModelWeights:
         out[140:160] = fold('tr_final_layer.0.weight', 'tr_final_layer.0.bias', 1, 21)
         out[160:180] = fold('rot_final_layer.0.weight', 'rot_final_layer.0.bias', 1, 21)
         tr_s, rot_s, tor_s = self.t_to_sigma(t)
-        out[180] = 1.0 / np.float32(tr_s)
+        out[180] = float(np.float32(1.0) / np.float32(tr_s))
         out[181] = float(np.asarray(so3_norm(np.asarray([rot_s], dtype=np.float32)))[0])
         out[182] = float(np.sqrt(np.float32(np.asarray(torus_norm(np.asarray([tor_s], dtype=np.float32)))[0])))
         if dt is not None:
