@@ -171,7 +171,7 @@ def main():
     for _ in range(args.warmup):
         sampler.reset(resident, generator=gen)
         sampler.run_resident(resident, generator=gen)
-        gather_poses(resident[-1][0].pos)
+        gather_poses(torch.cat([r[0].pos for r in resident]))
     barrier()
     prof = profiling.KernelTimer()
     clocks = ClockSampler(local)
@@ -184,7 +184,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         sampler.run_resident(resident, generator=gen, timer=prof)
-        gather_poses(resident[-1][0].pos)
+        gather_poses(torch.cat([r[0].pos for r in resident]))
         e1.record()
         barrier()
         times.append(e0.elapsed_time(e1))

@@ -230,7 +230,7 @@ class PackedBatch:
         S = samples_per_graph
         pa = [_pair_arrays(g) for g in graphs]
         B = len(pa) * S
-        self.B, self.S, self.device = B, S, device
+        self.B, self.S, self.device = B, S, device = B, S, torch.device(device)
         rep = lambda arrs: np.concatenate([np.tile(a, (S,) + (1,) * (a.ndim - 1)) for a in arrs], 0)
         n_per = np.repeat([p.n for p in pa], S)
         P_per = np.repeat([p.P for p in pa], S)
@@ -275,8 +275,16 @@ class PackedBatch:
                 masks.append(p.mask.reshape(-1))
                 moff.append(moff[-1] + p.mask.size)
                 gi += 1
-        i32 = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.int32))).to(device)
-        f32 = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32))).to(device)
+        self.h2d_bytes = 0
+
+        def up(t):
+            self.h2d_bytes += t.numel() * t.element_size()
+            if device.type == 'cuda':
+                return t.pin_memory().to(device, non_blocking=True)
+            return t.to(device)
+
+        i32 = lambda a: up(torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.int32))))
+        f32 = lambda a: up(torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32))))
         cat = lambda l, dt: np.concatenate(l).astype(dt) if len(l) else np.zeros(0, dt)
         self.lig_ptr, self.ph_ptr, self.rot_ptr = i32(lig_ptr), i32(ph_ptr), i32(rot_ptr)
         self.lig_batch = i32(np.repeat(np.arange(B), n_per))
@@ -293,15 +301,15 @@ class PackedBatch:
         # CSR of cross edges by ligand atom (canonical order) and by phore node (transposed order)
         self.cross_seg_lig = i32(np.concatenate([[0], np.cumsum(np.repeat(P_per, n_per))]))
         self.cross_seg_ph = i32(np.concatenate([[0], np.cumsum(np.repeat(n_per, P_per))]))
-        self.mask = torch.from_numpy(cat(masks, np.uint8)).to(device)
-        self.mask_off = torch.from_numpy(np.asarray(moff[:-1], dtype=np.int64)).to(device)
+        self.mask = up(torch.from_numpy(cat(masks, np.uint8)))
+        self.mask_off = up(torch.from_numpy(np.asarray(moff[:-1], dtype=np.int64)))
         self.lig_arange = torch.arange(self.n_lig, dtype=torch.int32, device=device)
         # node-level tensors
         self.pos = f32(rep([p.pos for p in pa]))
         self.norm = f32(rep([p.norm for p in pa]))
         self.phorefp, self.na1, self.na2 = f32(rep([p.phorefp for p in pa])), f32(rep([p.na1 for p in pa])), f32(rep([p.na2 for p in pa]))
         self.ppos, self.pnorm, self.ptype = f32(rep([p.ppos for p in pa])), f32(rep([p.pnorm for p in pa])), f32(rep([p.ptype for p in pa]))
-        x = torch.from_numpy(rep([p.x for p in pa])).to(device)
+        x = up(torch.from_numpy(rep([p.x for p in pa])))
         px = f32(rep([p.px for p in pa]))
         # static parts of the AtomEncoders (setup-time gathers; smp:64-73)
         w = weights
@@ -322,7 +330,7 @@ class PackedBatch:
 class Workspace:
     """All per-step device buffers for one PackedBatch."""
 
-    def __init__(self, b, weights):
+    def __init__(self, b, weights, wbuf=None):
         dev = b.device
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         i = lambda *s: torch.empty(*s, dtype=torch.int32, device=dev)
@@ -340,7 +348,8 @@ class Workspace:
         self.tor_feat = f(max(b.n_rot, 1), 40)
         self.tr, self.rot, self.tor = f(b.B, 3), f(b.B, 3), f(max(b.n_rot, 1))
         w_elems = max(b.ll_cap * 2200, b.n_cross * 2200, b.n_pp * 1600, b.tor_cap * 1600, b.n_lig * 200, 1)
-        self.wbuf = f(w_elems)
+        self.w_elems = w_elems
+        self.wbuf = wbuf if wbuf is not None and wbuf.numel() >= w_elems else f(w_elems)   # per-edge TP weights
         self.n_launches = 0
 
 
@@ -350,10 +359,13 @@ class Engine:
     def __init__(self, weights):
         self.w = weights
         self.lib = weights.lib
+        self.timer = None          # profiling.KernelTimer or None
 
-    def pack(self, graphs, samples_per_graph=1):
+    def pack(self, graphs, samples_per_graph=1, wbuf=None):
+        """Upload a batch and run the static-geometry setup kernels.  wbuf: optional shared per-edge weight buffer
+        (chunks run one after the other on one stream, so they can share it)."""
         b = PackedBatch(graphs, samples_per_graph, self.w, self.w.device)
-        ws = Workspace(b, self.w)
+        ws = Workspace(b, self.w, wbuf)
         st = torch.cuda.current_stream().cuda_stream
         sw = self.w.sw
         L.check(self.lib.dp_pp_setup(L.ptr(b.ppos), L.ptr(b.pp_src), L.ptr(b.pp_dst), b.n_pp, sw, L.ptr(ws.pp_h),
@@ -364,14 +376,27 @@ class Engine:
 
     # ------------------------------------------------------------------ one TensorProductConvLayer
     def _conv(self, cw, ws, emb, perm, tb, idxB, tc, idxC, idxC2, n_dev, n_cap, node_in, gather, sh, sh_stride, seg, out,
-              residual, res_dim, mode, n_out, st):
+              residual, res_dim, mode, n_out, st, name=''):
         p = L.ptr
+        tm = self.timer
+        if tm is not None:
+            n_rec = n_cap
+            if n_dev is not None:                       # dynamic edge count: stream-ordered copy to pinned memory
+                n_rec = torch.empty(1, dtype=torch.int32).pin_memory()
+                n_rec.copy_(n_dev, non_blocking=True)
+            e0 = tm.start()
         L.check(self.lib.dp_edge_mlp(p(emb), p(perm), p(tb), p(idxB), tb.shape[1], p(tc), p(idxC), p(idxC2),
                                      tc.shape[1] if tc is not None else 0, p(cw.w1), p(cw.b1), p(cw.w2t), cw.in_dim, cw.hid,
                                      cw.W, p(n_dev), n_cap, p(ws.wbuf), st), 'dp_edge_mlp')
+        if tm is not None:
+            tm.stop('edge_mlp', name, e0, n_rec, dict(in_dim=cw.in_dim, hid=cw.hid, W=cw.W))
+            e0 = tm.start()
         L.check(self.lib.dp_tp_scatter(cw.layer_id, p(node_in), p(gather), p(perm), p(sh), sh_stride, p(ws.wbuf), p(seg),
                                        p(cw.oscale), p(cw.oshift), p(out), p(residual), res_dim, mode, n_out, st),
                 'dp_tp_scatter')
+        if tm is not None:
+            tm.stop('tp_scatter', name, e0, n_rec, dict(W=cw.W, d_in=cw.d_in, d_out=cw.d_out, d_sh=sh_stride if sh_stride == 9 else 7,
+                                                        n_out=n_out))
         ws.n_launches += 2
 
     def forward(self, b, ws, sc):
@@ -396,25 +421,25 @@ class Engine:
             lh, ph, lo = ws.lig_h[l], ws.ph_h[l] if l < 4 else None, ws.lig_h[l + 1]
             d = LAYER_DIMS[l]
             self._conv(cv[('lig', l)], ws, ws.ll_emb, None, lh, ws.ll_src, lh, ws.ll_dst, None, ws.ll_n, b.ll_cap,
-                       lh, ws.ll_dst, ws.ll_sh, 9, ws.ll_ptr, lo, lh, d, 1, b.n_lig, st)
+                       lh, ws.ll_dst, ws.ll_sh, 9, ws.ll_ptr, lo, lh, d, 1, b.n_lig, st, f'lig{l}')
             self._conv(cv[('phore_to_lig', l)], ws, ws.cross_emb, None, lh, b.cross_lig, ph, b.cross_ph, None, None,
-                       b.n_cross, ph, b.cross_ph, ws.cross_sh, 9, b.cross_seg_lig, lo, None, 0, 2, b.n_lig, st)
+                       b.n_cross, ph, b.cross_ph, ws.cross_sh, 9, b.cross_seg_lig, lo, None, 0, 2, b.n_lig, st, f'p2l{l}')
             self._conv(cv[('phore_to_lig_norm', l)], ws, ws.cross_emb, None, lh, b.cross_lig, ph, b.cross_ph, None, None,
-                       b.n_cross, ph, b.cross_ph, ws.cross_nsh, 9, b.cross_seg_lig, lo, None, 0, 2, b.n_lig, st)
+                       b.n_cross, ph, b.cross_ph, ws.cross_nsh, 9, b.cross_seg_lig, lo, None, 0, 2, b.n_lig, st, f'p2ln{l}')
             if l != 3:
                 po = ws.ph_h[l + 1]
                 self._conv(cv[('phore', l)], ws, ws.pp_emb, None, ph, b.pp_src, ph, b.pp_dst, None, None, b.n_pp,
-                           ph, b.pp_dst, ws.pp_sh, 9, b.pp_ptr, po, ph, d, 1, b.n_ph, st)
+                           ph, b.pp_dst, ws.pp_sh, 9, b.pp_ptr, po, ph, d, 1, b.n_ph, st, f'pp{l}')
                 self._conv(cv[('lig_to_phore', l)], ws, ws.cross_emb, b.cross_perm_t, lh, b.cross_lig_t, ph, b.cross_ph_t,
                            None, None, b.n_cross, lh, b.cross_lig_t, ws.cross_sh, 9, b.cross_seg_ph, po, None, 0, 2,
-                           b.n_ph, st)
+                           b.n_ph, st, f'l2p{l}')
                 self._conv(cv[('lig_to_phore_norm', l)], ws, ws.cross_emb, b.cross_perm_t, lh, b.cross_lig_t, ph,
                            b.cross_ph_t, None, None, b.n_cross, lh, b.cross_lig_t, ws.cross_nsh, 9, b.cross_seg_ph, po,
-                           None, 0, 2, b.n_ph, st)
+                           None, 0, 2, b.n_ph, st, f'l2pn{l}')
         h4 = ws.lig_h[4]
         L.check(lib.dp_center_step(p(b.pos), p(b.lig_ptr), b.B, sw, scp, p(ws.c_emb), p(ws.c_sh), st), 'dp_center_step')
         self._conv(cv['final'], ws, ws.c_emb, None, h4, b.lig_arange, None, None, None, None, b.n_lig, h4, None, ws.c_sh, 9,
-                   b.lig_ptr, ws.gpred, None, 0, 0, b.B, st)
+                   b.lig_ptr, ws.gpred, None, 0, 0, b.B, st, 'final')
         L.check(lib.dp_score_head(p(ws.gpred), b.B, sw, scp, p(ws.tr), p(ws.rot), st), 'dp_score_head')
         ws.n_launches += 2
         if b.n_rot > 0:
@@ -422,7 +447,7 @@ class Engine:
                                      p(ws.deg), p(ws.gcount), p(ws.gstart), p(ws.t_ptr), p(ws.t_atom), p(ws.t_u), p(ws.t_v),
                                      p(ws.t_emb), p(ws.t_sh), p(ws.t_n), st), 'dp_tor_graph')
             self._conv(cv['tor'], ws, ws.t_emb, None, h4, ws.t_atom, h4, ws.t_u, ws.t_v, ws.t_n, b.tor_cap, h4, ws.t_atom,
-                       ws.t_sh, 8, ws.t_ptr, ws.tor_feat, None, 0, 0, b.n_rot, st)
+                       ws.t_sh, 8, ws.t_ptr, ws.tor_feat, None, 0, 0, b.n_rot, st, 'tor')
             L.check(lib.dp_tor_head(p(ws.tor_feat), b.n_rot, sw, scp, p(ws.tor), st), 'dp_tor_head')
             ws.n_launches += 4
         return ws.tr, ws.rot, ws.tor[:b.n_rot]

