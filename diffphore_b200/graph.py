@@ -109,12 +109,15 @@ def collate(data_list):
         counts = [s.num_nodes for s in stores]
         node_off[nt] = np.concatenate([[0], np.cumsum(counts)])
         dst = out[nt]
+        slices = {}
         for k in stores[0].keys():
             vals = [getattr(s, k) for s in stores]
-            if torch.is_tensor(vals[0]) and not (k == 'ph'):
+            if torch.is_tensor(vals[0]) and vals[0].dim() > 0:
                 setattr(dst, k, torch.cat(vals, 0))
+                slices[k] = np.concatenate([[0], np.cumsum([v.shape[0] for v in vals])]).tolist()
             else:
                 setattr(dst, k, vals)
+        dst._slices = slices            # like PyG's slice_dict: node stores may carry per-edge tensors (edge_mask)
         dst.batch = torch.repeat_interleave(torch.arange(len(data_list)), torch.tensor(counts))
         dst.ptr = torch.from_numpy(node_off[nt]).long()
     for et in data_list[0].edge_types:
@@ -145,12 +148,14 @@ def uncollate(batch):
     for nt in batch.node_types:
         src = batch[nt]
         ptr = src.ptr.tolist()
+        slices = getattr(src, '_slices', {})
         for k in src.keys():
-            if k in ('batch', 'ptr', 'node_t', 'node_sigma_emb'):
+            if k in ('batch', 'ptr', 'node_t', 'node_sigma_emb', '_slices'):
                 continue
             v = getattr(src, k)
+            sl = slices.get(k, ptr)
             for i, o in enumerate(outs):
-                setattr(o[nt], k, v[ptr[i]:ptr[i + 1]].clone() if torch.is_tensor(v) else v[i])
+                setattr(o[nt], k, v[sl[i]:sl[i + 1]].clone() if torch.is_tensor(v) else v[i])
     for et in batch.edge_types:
         src = batch[et]
         eptr = src.ptr.tolist()

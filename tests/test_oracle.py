@@ -234,3 +234,22 @@ def test_conformer_update_oracle_properties():
     assert torch.allclose(d0, d1, atol=1e-5)
     assert torch.allclose(g2['ligand'].pos.mean(0) - c0, tr[0], atol=1e-5)
     assert g2['ligand'].norm.shape == (14, 33)
+
+
+def test_oracle_sampling_loop_runs_and_is_deterministic():
+    """sampling_phore restatement end to end (2 steps, per-step re-collation through collate/to_data_list)."""
+    from oracle.model import default_config
+    sd = random_state_dict(0)
+    graphs = load_pairs('synthetic', 2, 8, 4)
+    init, noise, n_rot = make_draws(graphs, 2, 1, steps=2)
+    tabs = (So3ScoreNorm(), TorusScoreNorm())
+    outs = []
+    for _ in range(2):
+        dl = oracle_initial_graphs(graphs, 2, init, n_rot)
+        res = osamp.sampling(dl, OracleScoreModel(sd, *tabs), 2, default_config(), collate, batch_size=2, noise=noise)
+        outs.append(torch.cat([g['ligand'].pos for g in res]))
+        assert len(res) == 4 and res[0]['ligand'].edge_mask.shape[0] == graphs[0]['ligand', 'ligand'].edge_index.shape[1]
+    assert torch.equal(outs[0], outs[1]) and torch.isfinite(outs[0]).all()
+    res0 = osamp.sampling(oracle_initial_graphs(graphs, 2, init, n_rot), OracleScoreModel(sd, *tabs), 2, default_config(),
+                          collate, batch_size=3, noise=None)
+    assert not torch.equal(torch.cat([g['ligand'].pos for g in res0]), outs[0])       # no_random differs from noisy run
