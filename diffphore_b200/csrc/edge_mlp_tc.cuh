@@ -1,0 +1,276 @@
+// dp_edge_mlp (tensor-core path): the same per-edge weight MLP as edge_mlp.cuh, with the second (97 % of FLOPs)
+// layer  w[128 edges, W] = h[128, 64] . W2aug[64, W]  on the 5th-gen tensor cores:
+//   tcgen05.mma.cta_group::1.kind::tf32, M=128, N=128, K=8, accumulators in TMEM (2 stages x 128 columns),
+//   operands in shared memory in the canonical K-major no-swizzle core-matrix layout (8 rows x 16 B),
+//   B (second-layer weights, bias folded in as K row 60) streamed per 128-column chunk by cp.async.bulk (TMA, 1-D)
+//   into a 2-stage ring, mbarrier full/empty pipeline, one elected thread issues the MMAs, 4 warps drain TMEM
+//   with tcgen05.ld (thread = edge row) and store to HBM.
+// fp32 parity: both operands are split x = hi + lo with hi = tf32(x) (round-to-nearest) and three MMAs
+// hi*hi + hi*lo + lo*hi are accumulated in fp32 ("3xTF32"), relative error ~2^-21 per product.
+// With 3 x 8 MMAs per chunk the tensor pipe needs ~1.6k clk per 128x128 chunk while the 64 KB of output need
+// ~4k clk of this SM's share of HBM write bandwidth: the kernel is HBM-write-bound by design.
+#pragma once
+#include "common.cuh"
+#include "edge_mlp.cuh"
+
+#define TC_THREADS 160              // warps 0-3: one thread per edge row; warp 4: TMEM owner, TMA + MMA issuer
+#define TC_BN 128                   // columns per chunk
+#define TC_K 64                     // padded hidden (+bias) dimension
+#define TC_OPER_BYTES (128 * TC_K * 4)          // one 128 x 64 fp32 operand tile = 32 KB
+#define TC_SMEM_BYTES (2 * TC_OPER_BYTES + 2 * 2 * TC_OPER_BYTES + 60 * 60 * 4 + 64 * 4 + 256)
+
+__device__ __forceinline__ uint32_t tc_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tc_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem(bar)), "r"(count));
+}
+__device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol bug traps (-> CUDA error reported through the ABI) instead of hanging the GPU
+__device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = tc_smem(bar);
+    for (uint32_t it = 0; it < (1u << 28); ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void tc_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc_smem(dst)),
+                 "l"(src), "r"(bytes), "r"(tc_smem(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem(bar)) : "memory");
+}
+// K-major, no swizzle: core matrix = 8 rows x 16 B contiguous; SBO = bytes between 8-row groups, LBO = bytes
+// between the two 16-B K chunks an MMA (K = 8 tf32) consumes.  (cute/arch/mma_sm100_desc.hpp SmemDescriptor)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;          // descriptor version (Blackwell)
+    return d;                        // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void tc_tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ float tc_tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+struct EdgeMlpTcArgs {
+    EdgeMlpArgs base;        // w2t unused here
+    const float* w2img;      // [nchunks][2 (hi, lo)][16 k-chunks][16 row groups][8 rows][4] fp32, zero padded
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArgs args) {
+    extern __shared__ __align__(128) uint8_t tc_smem_raw[];
+    const EdgeMlpArgs& a = args.base;
+    float* a_hi = reinterpret_cast<float*>(tc_smem_raw);
+    float* a_lo = a_hi + 128 * TC_K;
+    float* b_st = a_lo + 128 * TC_K;                       // 2 stages x (hi 32 KB | lo 32 KB)
+    float* w1s = b_st + 2 * 2 * 128 * TC_K;                // [60][60]
+    float* b1s = w1s + 3600;                               // [64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b1s + 64);   // b_full[2], b_empty[2], t_full[2], t_empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t *b_full = bars, *b_empty = bars + 2, *t_full = bars + 4, *t_empty = bars + 6;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int E = a.n_edges_dev ? *a.n_edges_dev : a.n_edges;
+    const int e0 = blockIdx.x * 128;
+    if (e0 >= E) return;
+    const int W = a.W, nchunks = (W + TC_BN - 1) / TC_BN;
+
+    for (int i = tid; i < 3600; i += TC_THREADS) w1s[i] = a.w1[i];
+    for (int i = tid; i < 60; i += TC_THREADS) b1s[i] = a.b1[i];
+    if (tid == 0) {
+        tc_mbar_init(&b_full[0], 1); tc_mbar_init(&b_full[1], 1);
+        tc_mbar_init(&b_empty[0], 1); tc_mbar_init(&b_empty[1], 1);
+        tc_mbar_init(&t_full[0], 1); tc_mbar_init(&t_full[1], 1);
+        tc_mbar_init(&t_empty[0], 128); tc_mbar_init(&t_empty[1], 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(tc_smem(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    // control thread starts streaming the first weight chunk while the workers build the A operand
+    if (tid == 128) {
+        tc_mbar_expect_tx(&b_full[0], 2 * TC_OPER_BYTES);
+        tc_bulk_load(b_st, args.w2img, 2 * TC_OPER_BYTES, &b_full[0]);
+    }
+    if (warp < 4) {
+        // ---- gather this thread's edge attributes (row = tid) and run the first layer on CUDA cores
+        const int e = min(e0 + tid, E - 1);
+        float x[60];
+        {
+            const int r = a.perm ? a.perm[e] : e;
+            const float2* p0 = reinterpret_cast<const float2*>(a.emb + (size_t)r * 20);
+            const float2* p1 = reinterpret_cast<const float2*>(a.tb + (size_t)a.idxB[e] * a.strideB);
+            const float2* p2 = reinterpret_cast<const float2*>(a.tc + (size_t)a.idxC[e] * a.strideC);
+#pragma unroll
+            for (int c = 0; c < 10; ++c) {
+                float2 v0 = p0[c], v1 = p1[c], v2 = p2[c];
+                x[2 * c] = v0.x; x[2 * c + 1] = v0.y;
+                x[20 + 2 * c] = v1.x; x[21 + 2 * c] = v1.y;
+                x[40 + 2 * c] = v2.x; x[41 + 2 * c] = v2.y;
+            }
+            if (a.idxC2) {
+                const float2* p3 = reinterpret_cast<const float2*>(a.tc + (size_t)a.idxC2[e] * a.strideC);
+#pragma unroll
+                for (int c = 0; c < 10; ++c) { float2 v = p3[c]; x[40 + 2 * c] += v.x; x[41 + 2 * c] += v.y; }
+            }
+        }
+        // A operand, K-major core-matrix layout: element (row, k) at  (k/4)*2048 + (row/8)*128 + (row%8)*16 + (k%4)*4 bytes
+        const int row_off = (tid >> 3) * 32 + (tid & 7) * 4;       // in floats
+#pragma unroll 1
+        for (int kc = 0; kc < 16; ++kc) {
+            float h[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = kc * 4 + j;
+                float s = 0.f;
+                if (k < 60) {
+                    s = b1s[k];
+                    const float4* wr = reinterpret_cast<const float4*>(w1s + k * 60);
+#pragma unroll
+                    for (int c = 0; c < 15; ++c) {
+                        const float4 wv = wr[c];
+                        s = fmaf(x[4 * c], wv.x, s); s = fmaf(x[4 * c + 1], wv.y, s);
+                        s = fmaf(x[4 * c + 2], wv.z, s); s = fmaf(x[4 * c + 3], wv.w, s);
+                    }
+                    s = fmaxf(s, 0.f);
+                } else if (k == 60) {
+                    s = 1.0f;                                   // bias row of W2aug
+                }
+                h[j] = s;
+            }
+            float4 hi = make_float4(tc_tf32_rna(h[0]), tc_tf32_rna(h[1]), tc_tf32_rna(h[2]), tc_tf32_rna(h[3]));
+            float4 lo = make_float4(h[0] - hi.x, h[1] - hi.y, h[2] - hi.z, h[3] - hi.w);
+            *reinterpret_cast<float4*>(a_hi + kc * 512 + row_off) = hi;
+            *reinterpret_cast<float4*>(a_lo + kc * 512 + row_off) = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy (MMA) reads
+    }
+    __syncthreads();
+
+    if (tid == 128) {
+        // ================= TMA producer + MMA issuer (single thread) =================
+        // instruction descriptor: D=F32, A=B=TF32, K-major both, N=128, M=128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t a_hi_s = tc_smem(a_hi), a_lo_s = tc_smem(a_lo);
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c & 1, u = c >> 1;
+            if (c + 1 < nchunks) {
+                const int s1 = (c + 1) & 1, u1 = (c + 1) >> 1;
+                tc_mbar_wait(&b_empty[s1], (u1 & 1) ^ 1);
+                tc_mbar_expect_tx(&b_full[s1], 2 * TC_OPER_BYTES);
+                tc_bulk_load(b_st + s1 * 2 * 128 * TC_K, args.w2img + (size_t)(c + 1) * 2 * 128 * TC_K, 2 * TC_OPER_BYTES,
+                             &b_full[s1]);
+            }
+            tc_mbar_wait(&b_full[s], u & 1);
+            tc_mbar_wait(&t_empty[s], (u & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t b_hi_s = tc_smem(b_st + s * 2 * 128 * TC_K), b_lo_s = b_hi_s + TC_OPER_BYTES;
+            const uint32_t d = tmem_base + (uint32_t)(s * TC_BN);
+#pragma unroll
+            for (int combo = 0; combo < 3; ++combo) {
+                const uint32_t as = combo == 2 ? a_lo_s : a_hi_s;
+                const uint32_t bs = combo == 1 ? b_lo_s : b_hi_s;
+#pragma unroll
+                for (int ks = 0; ks < TC_K / 8; ++ks) {
+                    const uint64_t ad = tc_smem_desc(as + ks * 2 * 2048, 2048, 128);
+                    const uint64_t bd = tc_smem_desc(bs + ks * 2 * 2048, 2048, 128);
+                    tc_mma_tf32(d, ad, bd, idesc, (combo | ks) ? 1u : 0u);
+                }
+            }
+            tc_commit(&b_empty[s]);       // smem stage reusable once these MMAs have read it
+            tc_commit(&t_full[s]);        // accumulator stage complete
+        }
+    } else if (warp < 4) {
+        // ================= epilogue: TMEM -> registers -> HBM (thread = edge row) =================
+        const int e = e0 + tid;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c & 1, u = c >> 1;
+            tc_mbar_wait(&t_full[s], u & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int q = 0; q < TC_BN / 32; ++q) {
+                float v[32];
+                tc_tmem_ld32(lane_base + (uint32_t)(s * TC_BN + q * 32), v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int n0 = c * TC_BN + q * 32;
+                if (e < E && n0 < W) {
+                    float* orow = a.out + (size_t)e * W + n0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (n0 + 4 * j < W)
+                            *reinterpret_cast<float4*>(orow + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            tc_mbar_arrive(&t_empty[s]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+static int edge_mlp_tc_launch(const EdgeMlpTcArgs& t, cudaStream_t st) {
+    const EdgeMlpArgs& a = t.base;
+    if (a.n_edges <= 0) return DP_OK;
+    if (a.in_dim != 60 || a.hid != 60 || (a.W % 4) != 0 || t.w2img == nullptr || a.tc == nullptr) {
+        dp_set_error("dp_edge_mlp_tc: unsupported shape in=%d hid=%d W=%d", a.in_dim, a.hid, a.W);
+        return DP_ERR_ARG;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(edge_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        attr_set = true;
+    }
+    dim3 grid((a.n_edges + 127) / 128);
+    edge_mlp_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(t);
+    return dp_check_launch("edge_mlp_tc");
+}

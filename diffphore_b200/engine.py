@@ -40,6 +40,10 @@ def sinusoidal_embedding(t, dim=20, scale=10000.0, max_positions=10000):
 class ConvWeights:
     """One TensorProductConvLayer (smp:76-149) prepared for dp_edge_mlp / dp_tp_scatter."""
 
+    @staticmethod
+    def make_w2img(w3, b3):
+        return _make_w2img(w3, b3)
+
     def __init__(self, sd, prefix, layer_id, in_irreps, sh_ir, out_irreps, device):
         instrs, numel = fctp_instructions(in_irreps, sh_ir, out_irreps)
         w3 = sd[prefix + '.fc.3.weight']
@@ -50,6 +54,7 @@ class ConvWeights:
         self.w1 = _f32(sd[prefix + '.fc.0.weight']).to(device)
         self.b1 = _f32(sd[prefix + '.fc.0.bias']).to(device)
         self.w2t = torch.cat([_f32(w3).T, _f32(sd[prefix + '.fc.3.bias'])[None, :]], 0).contiguous().to(device)
+        self.w2img = self.make_w2img(_f32(w3), _f32(sd[prefix + '.fc.3.bias'])).to(device) if self.hid == 60 and self.in_dim == 60 else None
         # eval BatchNorm (e3nn.nn.BatchNorm) and path weights folded into per-component scale/shift
         bw, bb = sd[prefix + '.batch_norm.weight'].double(), sd[prefix + '.batch_norm.bias'].double()
         rm, rv = sd[prefix + '.batch_norm.running_mean'].double(), sd[prefix + '.batch_norm.running_var'].double()
@@ -71,6 +76,22 @@ class ConvWeights:
         self.oscale = torch.cat(scale).float().contiguous().to(device)
         self.oshift = torch.cat(shift).float().contiguous().to(device)
         self.d_in, self.d_out = irreps_dim(in_irreps), irreps_dim(out_irreps)
+
+
+def _make_w2img(w3, b3):
+    """Shared-memory image of the second-layer weights for dp_edge_mlp_tc: W2aug[n, 0:60] = fc.3.weight, [n, 60] = bias,
+    zero padded to K = 64 and to a multiple of 128 columns, split into tf32 hi (round-to-nearest-away, like
+    cvt.rna.tf32.f32) and the fp32 remainder lo, stored per 128-column chunk as [hi|lo][k/4][n/8][n%8][k%4]."""
+    W = w3.shape[0]
+    nch = (W + 127) // 128
+    x = torch.zeros(nch * 128, 64, dtype=torch.float32)
+    x[:W, :60] = w3
+    x[:W, 60] = b3
+    bits = x.view(torch.int32)
+    hi = ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+    lo = x - hi
+    img = torch.stack([hi, lo], 0).reshape(2, nch, 16, 8, 16, 4).permute(1, 0, 4, 2, 3, 5)     # [c][h][kc][ng][r][j]
+    return img.contiguous().reshape(-1)
 
 
 class ModelWeights:
@@ -360,6 +381,9 @@ class Engine:
         self.w = weights
         self.lib = weights.lib
         self.timer = None          # profiling.KernelTimer or None
+        # second MLP layer on tcgen05 tensor cores (3xTF32) or on CUDA cores (FFMA); env DIFFPHORE_EDGE_MLP=ffma|tc
+        import os
+        self.use_tc = os.environ.get('DIFFPHORE_EDGE_MLP', 'ffma') == 'tc'
 
     def pack(self, graphs, samples_per_graph=1, wbuf=None):
         """Upload a batch and run the static-geometry setup kernels.  wbuf: optional shared per-edge weight buffer
@@ -385,9 +409,14 @@ class Engine:
                 n_rec = torch.empty(1, dtype=torch.int32).pin_memory()
                 n_rec.copy_(n_dev, non_blocking=True)
             e0 = tm.start()
-        L.check(self.lib.dp_edge_mlp(p(emb), p(perm), p(tb), p(idxB), tb.shape[1], p(tc), p(idxC), p(idxC2),
-                                     tc.shape[1] if tc is not None else 0, p(cw.w1), p(cw.b1), p(cw.w2t), cw.in_dim, cw.hid,
-                                     cw.W, p(n_dev), n_cap, p(ws.wbuf), st), 'dp_edge_mlp')
+        if self.use_tc and cw.w2img is not None:
+            L.check(self.lib.dp_edge_mlp_tc(p(emb), p(perm), p(tb), p(idxB), tb.shape[1], p(tc), p(idxC), p(idxC2), tc.shape[1],
+                                            p(cw.w1), p(cw.b1), p(cw.w2img), cw.in_dim, cw.hid, cw.W, p(n_dev), n_cap,
+                                            p(ws.wbuf), st), 'dp_edge_mlp_tc')
+        else:
+            L.check(self.lib.dp_edge_mlp(p(emb), p(perm), p(tb), p(idxB), tb.shape[1], p(tc), p(idxC), p(idxC2),
+                                         tc.shape[1] if tc is not None else 0, p(cw.w1), p(cw.b1), p(cw.w2t), cw.in_dim,
+                                         cw.hid, cw.W, p(n_dev), n_cap, p(ws.wbuf), st), 'dp_edge_mlp')
         if tm is not None:
             tm.stop('edge_mlp', name, e0, n_rec, dict(in_dim=cw.in_dim, hid=cw.hid, W=cw.W))
             e0 = tm.start()

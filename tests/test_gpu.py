@@ -214,3 +214,35 @@ def test_abi_error_behaviour(built_lib):
     assert rc != 0 and b'unknown layer' in lib.dp_last_error()
     rc = lib.dp_edge_mlp(None, None, None, None, 20, None, None, None, 20, None, None, None, 50, 60, 600, None, 10, None, None)
     assert rc != 0
+
+
+@pytest.mark.parametrize('W,E', [(600, 1000), (2200, 777), (1100, 128)])
+def test_edge_mlp_tensor_core_path_matches_ffma_path(built_lib, W, E):
+    """dp_edge_mlp_tc (tcgen05, 3xTF32) against dp_edge_mlp (FP32 FFMA) and a float64 torch evaluation."""
+    from diffphore_b200.engine import _make_w2img
+    lib, p = built_lib.load(), built_lib.ptr
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(W + E)
+    n_nodes = 300
+    emb = torch.randn(E, 20, generator=g).to(dev)
+    nb, nc = (torch.randn(n_nodes, 50, generator=g) * 3).to(dev), (torch.randn(n_nodes, 80, generator=g) * 3).to(dev)
+    ib = torch.randint(0, n_nodes, (E,), generator=g, dtype=torch.int32).to(dev)
+    ic = torch.randint(0, n_nodes, (E,), generator=g, dtype=torch.int32).to(dev)
+    w1, b1 = (torch.randn(60, 60, generator=g) * 0.2).to(dev), torch.randn(60, generator=g).to(dev)
+    w3, b3 = torch.randn(W, 60, generator=g) * 0.5, torch.randn(W, generator=g)
+    w2t = torch.cat([w3.T, b3[None]], 0).contiguous().to(dev)
+    img = _make_w2img(w3, b3).to(dev)
+    n_dev = torch.tensor([E], dtype=torch.int32, device=dev)
+    out_f, out_t = torch.zeros(E + 5, W, device=dev), torch.full((E + 5, W), 7.0, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    built_lib.check(lib.dp_edge_mlp(p(emb), None, p(nb), p(ib), 50, p(nc), p(ic), None, 80, p(w1), p(b1), p(w2t), 60, 60, W,
+                                    p(n_dev), E + 200, p(out_f), st))
+    built_lib.check(lib.dp_edge_mlp_tc(p(emb), None, p(nb), p(ib), 50, p(nc), p(ic), None, 80, p(w1), p(b1), p(img), 60, 60, W,
+                                       p(n_dev), E + 200, p(out_t), st))
+    torch.cuda.synchronize()
+    attr = torch.cat([emb, nb[ib.long(), :20], nc[ic.long(), :20]], 1).double()
+    ref = torch.relu(attr @ w1.double().T + b1.double()) @ w3.double().to(dev).T + b3.double().to(dev)
+    assert rel(out_f[:E].cpu(), ref.cpu()) < 2e-6
+    assert rel(out_t[:E].cpu(), ref.cpu()) < 2e-6, rel(out_t[:E].cpu(), ref.cpu())
+    assert float((out_t[:E] - ref).abs().max() / ref.abs().max()) < 5e-6
+    assert bool((out_t[E:] == 7.0).all())                    # rows beyond the device-side edge count are untouched
