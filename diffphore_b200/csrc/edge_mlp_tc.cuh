@@ -17,7 +17,8 @@
 #define TC_BN 128                   // columns per chunk
 #define TC_K 64                     // padded hidden (+bias) dimension
 #define TC_OPER_BYTES (128 * TC_K * 4)          // one 128 x 64 fp32 operand tile = 32 KB
-#define TC_SMEM_BYTES (2 * TC_OPER_BYTES + 2 * 2 * TC_OPER_BYTES + 60 * 60 * 4 + 64 * 4 + 256)
+#define TC_STG_LD 36                // padded row length (floats) of the per-warp 32x32 transpose tile
+#define TC_SMEM_BYTES (2 * TC_OPER_BYTES + 2 * 2 * TC_OPER_BYTES + 60 * 60 * 4 + 64 * 4 + 256 + 4 * 32 * TC_STG_LD * 4)
 
 __device__ __forceinline__ uint32_t tc_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
     float* b1s = w1s + 3600;                               // [64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(b1s + 64);   // b_full[2], b_empty[2], t_full[2], t_empty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    float* stg_all = reinterpret_cast<float*>(bars) + 64;       // 256 B after the barriers: 4 x [32][36] transpose tiles
     uint64_t *b_full = bars, *b_empty = bars + 2, *t_full = bars + 4, *t_empty = bars + 6;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -226,9 +228,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
             tc_commit(&t_full[s]);        // accumulator stage complete
         }
     } else if (warp < 4) {
-        // ================= epilogue: TMEM -> registers -> HBM (thread = edge row) =================
-        const int e = e0 + tid;
+        // ================= epilogue: TMEM -> registers -> smem transpose -> coalesced HBM stores =================
+        // tcgen05.ld hands thread t the 32 columns of row t; a direct store would touch 32 different lines per
+        // instruction, so each warp transposes its 32x32 block through a private padded tile and stores 4 rows x 128
+        // contiguous bytes per instruction.
+        float* stg = stg_all + warp * 32 * TC_STG_LD;
         const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const int r_sub = lane >> 3, c_sub = (lane & 7) * 4;
         for (int c = 0; c < nchunks; ++c) {
             const int s = c & 1, u = c >> 1;
             tc_mbar_wait(&t_full[s], u & 1);
@@ -238,13 +244,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
                 float v[32];
                 tc_tmem_ld32(lane_base + (uint32_t)(s * TC_BN + q * 32), v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const int n0 = c * TC_BN + q * 32;
-                if (e < E && n0 < W) {
-                    float* orow = a.out + (size_t)e * W + n0;
+                __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (n0 + 4 * j < W)
-                            *reinterpret_cast<float4*>(orow + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(stg + lane * TC_STG_LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                __syncwarp();
+                const int n0 = c * TC_BN + q * 32 + c_sub;
+                if (n0 < W) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = 4 * i + r_sub;
+                        const int e = e0 + warp * 32 + r;
+                        const float4 o = *reinterpret_cast<const float4*>(stg + r * TC_STG_LD + c_sub);
+                        if (e < E) *reinterpret_cast<float4*>(a.out + (size_t)e * W + n0) = o;
+                    }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

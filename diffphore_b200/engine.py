@@ -383,7 +383,7 @@ class Engine:
         self.timer = None          # profiling.KernelTimer or None
         # second MLP layer on tcgen05 tensor cores (3xTF32) or on CUDA cores (FFMA); env DIFFPHORE_EDGE_MLP=ffma|tc
         import os
-        self.use_tc = os.environ.get('DIFFPHORE_EDGE_MLP', 'ffma') == 'tc'
+        self.use_tc = os.environ.get('DIFFPHORE_EDGE_MLP', 'tc') == 'tc'
 
     def pack(self, graphs, samples_per_graph=1, wbuf=None):
         """Upload a batch and run the static-geometry setup kernels.  wbuf: optional shared per-edge weight buffer
