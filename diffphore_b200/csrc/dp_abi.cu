@@ -2,10 +2,12 @@
 // Single translation unit: all kernels are included here so that constant memory and templates link trivially.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 #include "tp_scatter.cuh"
 #include "edge_mlp.cuh"
 #include "edge_mlp_tc.cuh"
+#include "tp_scatter_tma.cuh"
 #include "graph_kernels.cuh"
 #include "conformer.cuh"
 
@@ -135,17 +137,26 @@ int dp_tp_scatter(int32_t layer, const float* node_in, const int32_t* gather_idx
                   int32_t sh_stride, const float* w, const int32_t* seg_ptr, const float* oscale, const float* oshift,
                   float* out, const float* residual, int32_t res_dim, int32_t mode, int32_t n_out, void* stream) {
     NEED(mode != 1 || residual != nullptr, "dp_tp_scatter: mode 1 needs a residual");
-#define TP_CASE(ID, CFG)                                                                                              \
+    static int use_tma = -1;                      // DIFFPHORE_TP_SCATTER=reg selects the register-streamed kernel
+    if (use_tma < 0) {
+        const char* e = getenv("DIFFPHORE_TP_SCATTER");
+        use_tma = (e && e[0] == 'r') ? 0 : 1;
+    }
+#define TP_CASE(ID, CFG, WARPS, STAGES)                                                                               \
     case ID:                                                                                                          \
+        if (use_tma)                                                                                                  \
+            return tp_scatter_tma_launch<CFG, WARPS, STAGES>(node_in, gather_idx, perm, sh, sh_stride, w, seg_ptr,    \
+                                                             oscale, oshift, out, residual, res_dim, mode, n_out,     \
+                                                             ST(stream));                                             \
         return tp_scatter_launch<CFG>(node_in, gather_idx, perm, sh, sh_stride, w, seg_ptr, oscale, oshift, out,      \
                                       residual, res_dim, mode, n_out, ST(stream));
     switch (layer) {
-        TP_CASE(DP_TP_L0, TpL0)
-        TP_CASE(DP_TP_L1, TpL1)
-        TP_CASE(DP_TP_L2, TpL2)
-        TP_CASE(DP_TP_L3, TpL3)
-        TP_CASE(DP_TP_FINAL, TpFinal)
-        TP_CASE(DP_TP_TOR, TpTor)
+        TP_CASE(DP_TP_L0, TpL0, 8, 8)
+        TP_CASE(DP_TP_L1, TpL1, 8, 4)
+        TP_CASE(DP_TP_L2, TpL2, 8, 3)
+        TP_CASE(DP_TP_L3, TpL3, 6, 3)
+        TP_CASE(DP_TP_FINAL, TpFinal, 8, 8)
+        TP_CASE(DP_TP_TOR, TpTor, 8, 3)
     }
     dp_set_error("dp_tp_scatter: unknown layer %d", layer);
     return DP_ERR_ARG;

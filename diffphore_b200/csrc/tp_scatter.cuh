@@ -20,7 +20,7 @@
 
 #define TP_WARPS 4
 
-template <class Cfg, int P>
+template <class Cfg, int P, bool X_IN_SMEM = false>
 __device__ __forceinline__ void tp_compute_z(const float* __restrict__ x, const float* sh, float (*zb)[4], int lane) {
     if constexpr (P < Cfg::NP) {
         constexpr TpPath p = Cfg::paths[P];
@@ -29,16 +29,16 @@ __device__ __forceinline__ void tp_compute_z(const float* __restrict__ x, const 
         if (lane < p.U) {
             float xv[3], z[3];
 #pragma unroll
-            for (int i = 0; i < D1; ++i) xv[i] = __ldg(x + p.in_off + lane * D1 + i);
+            for (int i = 0; i < D1; ++i) xv[i] = X_IN_SMEM ? x[p.in_off + lane * D1 + i] : __ldg(x + p.in_off + lane * D1 + i);
             dp_cg<p.l1, p.l2, LO>(xv, sh + p.sh_off, z);
 #pragma unroll
             for (int k = 0; k < 2 * LO + 1; ++k) zb[p.zoff + lane][k] = z[k];
         }
-        tp_compute_z<Cfg, P + 1>(x, sh, zb, lane);
+        tp_compute_z<Cfg, P + 1, X_IN_SMEM>(x, sh, zb, lane);
     }
 }
 
-template <class Cfg, int P>
+template <class Cfg, int P, bool W_IN_SMEM = false>
 __device__ __forceinline__ void tp_accumulate(const float* __restrict__ wrow, const float (*zb)[4],
                                               float (&acc)[Cfg::NO][2][3], int lane) {
     if constexpr (P < Cfg::NP) {
@@ -55,7 +55,10 @@ __device__ __forceinline__ void tp_accumulate(const float* __restrict__ wrow, co
             const bool ok = (lane < 30) && (row < p.U);
             const int r = ok ? row : 0;
             float2 wv = make_float2(0.f, 0.f);
-            if (ok) wv = __ldg(reinterpret_cast<const float2*>(wrow + p.w_off + r * V) + j);
+            if (ok) {
+                if constexpr (W_IN_SMEM) wv = *(reinterpret_cast<const float2*>(wrow + p.w_off + r * V) + j);
+                else wv = __ldg(reinterpret_cast<const float2*>(wrow + p.w_off + r * V) + j);
+            }
             if constexpr (K == 1) {
                 const float z0 = zb[p.zoff + r][0];
                 acc[p.oi][0][0] = fmaf(wv.x, z0, acc[p.oi][0][0]);
@@ -70,7 +73,7 @@ __device__ __forceinline__ void tp_accumulate(const float* __restrict__ wrow, co
                 acc[p.oi][1][2] = fmaf(wv.y, z.z, acc[p.oi][1][2]);
             }
         }
-        tp_accumulate<Cfg, P + 1>(wrow, zb, acc, lane);
+        tp_accumulate<Cfg, P + 1, W_IN_SMEM>(wrow, zb, acc, lane);
     }
 }
 
@@ -141,9 +144,9 @@ tp_scatter_kernel(const float* __restrict__ node_in, const int* __restrict__ gat
 #pragma unroll
         for (int i = 0; i < Cfg::SH_USED; ++i) shv[i] = __ldg(sh + (size_t)ce * sh_stride + i);
         __syncwarp();
-        tp_compute_z<Cfg, 0>(node_in + (size_t)src * Cfg::D_IN, shv, zb, lane);
+        tp_compute_z<Cfg, 0, false>(node_in + (size_t)src * Cfg::D_IN, shv, zb, lane);
         __syncwarp();
-        tp_accumulate<Cfg, 0>(w + (size_t)e * Cfg::W, zb, acc, lane);
+        tp_accumulate<Cfg, 0, false>(w + (size_t)e * Cfg::W, zb, acc, lane);
     }
     const int deg = e1 - e0;
     const float inv_deg = 1.0f / (float)(deg > 0 ? deg : 1);
