@@ -13,12 +13,13 @@
 #include "common.cuh"
 #include "edge_mlp.cuh"
 
-#define TC_THREADS 160              // warps 0-3: one thread per edge row; warp 4: TMEM owner, TMA + MMA issuer
+#define TC_WORKERS 256              // warps 0-7: two threads per edge row (row = tid & 127, half = tid >> 7)
+#define TC_THREADS 288              // + warp 8: TMEM owner, TMA + MMA issuer
 #define TC_BN 128                   // columns per chunk
 #define TC_K 64                     // padded hidden (+bias) dimension
 #define TC_OPER_BYTES (128 * TC_K * 4)          // one 128 x 64 fp32 operand tile = 32 KB
-#define TC_STG_LD 36                // padded row length (floats) of the per-warp 32x32 transpose tile
-#define TC_SMEM_BYTES (2 * TC_OPER_BYTES + 2 * 2 * TC_OPER_BYTES + 60 * 60 * 4 + 64 * 4 + 256 + 4 * 32 * TC_STG_LD * 4)
+// per-warp 32x32 fp32 transpose tiles (XOR-swizzled 16-B chunks) alias the first-layer weights, which are dead by then
+#define TC_SMEM_BYTES (2 * TC_OPER_BYTES + 2 * 2 * TC_OPER_BYTES + 8 * 32 * 32 * 4 + 64 * 4 + 256)
 
 __device__ __forceinline__ uint32_t tc_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -103,11 +104,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
     float* a_hi = reinterpret_cast<float*>(tc_smem_raw);
     float* a_lo = a_hi + 128 * TC_K;
     float* b_st = a_lo + 128 * TC_K;                       // 2 stages x (hi 32 KB | lo 32 KB)
-    float* w1s = b_st + 2 * 2 * 128 * TC_K;                // [60][60]
-    float* b1s = w1s + 3600;                               // [64]
+    float* w1s = b_st + 2 * 2 * 128 * TC_K;                // [60][60] during setup; 8 x [32][32] transpose tiles afterwards
+    float* stg_all = w1s;
+    float* b1s = w1s + 8 * 32 * 32;                        // [64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(b1s + 64);   // b_full[2], b_empty[2], t_full[2], t_empty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-    float* stg_all = reinterpret_cast<float*>(bars) + 64;       // 256 B after the barriers: 4 x [32][36] transpose tiles
     uint64_t *b_full = bars, *b_empty = bars + 2, *t_full = bars + 4, *t_empty = bars + 6;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -122,10 +123,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
         tc_mbar_init(&b_full[0], 1); tc_mbar_init(&b_full[1], 1);
         tc_mbar_init(&b_empty[0], 1); tc_mbar_init(&b_empty[1], 1);
         tc_mbar_init(&t_full[0], 1); tc_mbar_init(&t_full[1], 1);
-        tc_mbar_init(&t_empty[0], 128); tc_mbar_init(&t_empty[1], 128);
+        tc_mbar_init(&t_empty[0], TC_WORKERS); tc_mbar_init(&t_empty[1], TC_WORKERS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(tc_smem(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -135,13 +136,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
     const uint32_t tmem_base = *tmem_slot;
 
     // control thread starts streaming the first weight chunk while the workers build the A operand
-    if (tid == 128) {
+    if (tid == TC_WORKERS) {
         tc_mbar_expect_tx(&b_full[0], 2 * TC_OPER_BYTES);
         tc_bulk_load(b_st, args.w2img, 2 * TC_OPER_BYTES, &b_full[0]);
     }
-    if (warp < 4) {
-        // ---- gather this thread's edge attributes (row = tid) and run the first layer on CUDA cores
-        const int e = min(e0 + tid, E - 1);
+    const int row = tid & 127, half = tid >> 7;
+    if (warp < 8) {
+        // ---- gather this row's edge attributes and run half of the first layer (k in [32*half, 32*half+32)) on CUDA cores
+        const int e = min(e0 + row, E - 1);
         float x[60];
         {
             const int r = a.perm ? a.perm[e] : e;
@@ -162,9 +164,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
             }
         }
         // A operand, K-major core-matrix layout: element (row, k) at  (k/4)*2048 + (row/8)*128 + (row%8)*16 + (k%4)*4 bytes
-        const int row_off = (tid >> 3) * 32 + (tid & 7) * 4;       // in floats
+        const int row_off = (row >> 3) * 32 + (row & 7) * 4;       // in floats
 #pragma unroll 1
-        for (int kc = 0; kc < 16; ++kc) {
+        for (int kc = 8 * half; kc < 8 * half + 8; ++kc) {
             float h[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
     }
     __syncthreads();
 
-    if (tid == 128) {
+    if (tid == TC_WORKERS) {
         // ================= TMA producer + MMA issuer (single thread) =================
         // instruction descriptor: D=F32, A=B=TF32, K-major both, N=128, M=128
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -227,35 +229,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
             tc_commit(&b_empty[s]);       // smem stage reusable once these MMAs have read it
             tc_commit(&t_full[s]);        // accumulator stage complete
         }
-    } else if (warp < 4) {
+    } else if (warp < 8) {
         // ================= epilogue: TMEM -> registers -> smem transpose -> coalesced HBM stores =================
-        // tcgen05.ld hands thread t the 32 columns of row t; a direct store would touch 32 different lines per
-        // instruction, so each warp transposes its 32x32 block through a private padded tile and stores 4 rows x 128
-        // contiguous bytes per instruction.
-        float* stg = stg_all + warp * 32 * TC_STG_LD;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-        const int r_sub = lane >> 3, c_sub = (lane & 7) * 4;
+        // tcgen05.ld hands lane t the 32 columns of TMEM lane (row) 32*(warp%4)+t; a direct store would touch 32 lines
+        // per instruction, so each warp transposes its 32x32 block through a private XOR-swizzled tile and stores
+        // 4 rows x 128 contiguous bytes per instruction.  Warps 0-3 drain columns 0-63 of a chunk, warps 4-7 columns
+        // 64-127 (a warp may only touch the TMEM lane quarter warp%4).
+        float* stg = stg_all + warp * 32 * 32;
+        const int wq = warp & 3, colhalf = warp >> 2;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
+        const int r_sub = lane >> 3, c4 = lane & 7;
         for (int c = 0; c < nchunks; ++c) {
             const int s = c & 1, u = c >> 1;
             tc_mbar_wait(&t_full[s], u & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-            for (int q = 0; q < TC_BN / 32; ++q) {
+            for (int q = 2 * colhalf; q < 2 * colhalf + 2; ++q) {
                 float v[32];
                 tc_tmem_ld32(lane_base + (uint32_t)(s * TC_BN + q * 32), v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<float4*>(stg + lane * TC_STG_LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 __syncwarp();
-                const int n0 = c * TC_BN + q * 32 + c_sub;
+                const int n0 = c * TC_BN + q * 32 + c4 * 4;
                 if (n0 < W) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int r = 4 * i + r_sub;
-                        const int e = e0 + warp * 32 + r;
-                        const float4 o = *reinterpret_cast<const float4*>(stg + r * TC_STG_LD + c_sub);
+                        const int e = e0 + wq * 32 + r;
+                        const float4 o = *reinterpret_cast<const float4*>(stg + r * 32 + ((c4 ^ (r & 7)) << 2));
                         if (e < E) *reinterpret_cast<float4*>(a.out + (size_t)e * W + n0) = o;
                     }
                 }
@@ -266,7 +271,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
     }
 }
