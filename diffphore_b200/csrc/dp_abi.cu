@@ -133,6 +133,12 @@ int dp_edge_mlp_tc(const float* emb, const int32_t* perm, const float* tb, const
     return edge_mlp_tc_launch(t, ST(stream));
 }
 
+/* profiling aid (not part of the public header): route per-phase clock stamps of dp_edge_mlp_tc to a device buffer */
+int dp_debug_set_tc_probe(long long* buf) {
+    cudaError_t e = cudaMemcpyToSymbol(g_tc_dbg, &buf, sizeof(buf));
+    return e == cudaSuccess ? DP_OK : DP_ERR_CUDA;
+}
+
 int dp_tp_scatter(int32_t layer, const float* node_in, const int32_t* gather_idx, const int32_t* perm, const float* sh,
                   int32_t sh_stride, const float* w, const int32_t* seg_ptr, const float* oscale, const float* oshift,
                   float* out, const float* residual, int32_t res_dim, int32_t mode, int32_t n_out, void* stream) {

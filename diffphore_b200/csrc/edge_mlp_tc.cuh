@@ -93,6 +93,9 @@ __device__ __forceinline__ float tc_tf32_rna(float x) {
     return __uint_as_float(r);
 }
 
+__device__ long long* g_tc_dbg = nullptr;     // profiling aid: per-phase clock64() stamps of CTA 200 (tools/tc_phase_probe.py)
+#define TC_STAMP(i) do { if (g_tc_dbg && blockIdx.x == 200 && (tid & 127) == 0) g_tc_dbg[(tid >> 7) * 16 + (i)] = clock64(); } while (0)
+
 struct EdgeMlpTcArgs {
     EdgeMlpArgs base;        // w2t unused here
     const float* w2img;      // [nchunks][2 (hi, lo)][16 k-chunks][16 row groups][8 rows][4] fp32, zero padded
@@ -108,8 +111,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
     float* stg_all = w1s;
     float* b1s = w1s + 8 * 32 * 32;                        // [64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(b1s + 64);   // b_full[2], b_empty[2], t_full[2], t_empty[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);      // bars[8]; bars[9] = first-layer weights barrier
     uint64_t *b_full = bars, *b_empty = bars + 2, *t_full = bars + 4, *t_empty = bars + 6;
+    uint64_t& w_full = bars[9];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int E = a.n_edges_dev ? *a.n_edges_dev : a.n_edges;
@@ -117,13 +121,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
     if (e0 >= E) return;
     const int W = a.W, nchunks = (W + TC_BN - 1) / TC_BN;
 
-    for (int i = tid; i < 3600; i += TC_THREADS) w1s[i] = a.w1[i];
-    for (int i = tid; i < 60; i += TC_THREADS) b1s[i] = a.b1[i];
+    TC_STAMP(0);
     if (tid == 0) {
         tc_mbar_init(&b_full[0], 1); tc_mbar_init(&b_full[1], 1);
         tc_mbar_init(&b_empty[0], 1); tc_mbar_init(&b_empty[1], 1);
         tc_mbar_init(&t_full[0], 1); tc_mbar_init(&t_full[1], 1);
-        tc_mbar_init(&t_empty[0], TC_WORKERS); tc_mbar_init(&t_empty[1], TC_WORKERS);
+        tc_mbar_init(&w_full, 1);
+        tc_mbar_init(&t_empty[0], TC_WORKERS / 32); tc_mbar_init(&t_empty[1], TC_WORKERS / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) {
@@ -134,35 +138,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    TC_STAMP(1);
 
     // control thread starts streaming the first weight chunk while the workers build the A operand
     if (tid == TC_WORKERS) {
+        tc_mbar_expect_tx(&w_full, 3600 * 4 + 60 * 4);
+        tc_bulk_load(w1s, a.w1, 3600 * 4, &w_full);
+        tc_bulk_load(b1s, a.b1, 60 * 4, &w_full);
         tc_mbar_expect_tx(&b_full[0], 2 * TC_OPER_BYTES);
         tc_bulk_load(b_st, args.w2img, 2 * TC_OPER_BYTES, &b_full[0]);
     }
     const int row = tid & 127, half = tid >> 7;
     if (warp < 8) {
-        // ---- gather this row's edge attributes and run half of the first layer (k in [32*half, 32*half+32)) on CUDA cores
-        const int e = min(e0 + row, E - 1);
-        float x[60];
-        {
-            const int r = a.perm ? a.perm[e] : e;
-            const float2* p0 = reinterpret_cast<const float2*>(a.emb + (size_t)r * 20);
-            const float2* p1 = reinterpret_cast<const float2*>(a.tb + (size_t)a.idxB[e] * a.strideB);
-            const float2* p2 = reinterpret_cast<const float2*>(a.tc + (size_t)a.idxC[e] * a.strideC);
-#pragma unroll
-            for (int c = 0; c < 10; ++c) {
-                float2 v0 = p0[c], v1 = p1[c], v2 = p2[c];
-                x[2 * c] = v0.x; x[2 * c + 1] = v0.y;
-                x[20 + 2 * c] = v1.x; x[21 + 2 * c] = v1.y;
-                x[40 + 2 * c] = v2.x; x[41 + 2 * c] = v2.y;
+        // ---- gather the edge attributes and run half of the first layer (k in [32*half, 32*half+32)) on CUDA cores
+        // cooperative, coalesced gather of the 128 x 60 attribute tile into shared memory (aliases weight stage 1,
+        // idle until the main loop): 10 lanes fetch one 80-byte part as float2 -> a warp instruction touches ~4 lines
+        float* attr = b_st + 2 * 128 * TC_K;                         // [128][61]
+        for (int i = tid; i < 128 * 30; i += TC_WORKERS) {
+            const int m = i / 30, q = i % 30, part = q / 10, c = (q % 10) * 2;
+            const int e = min(e0 + m, E - 1);
+            float2 v;
+            if (part == 0) {
+                const int r = a.perm ? a.perm[e] : e;
+                v = *reinterpret_cast<const float2*>(a.emb + (size_t)r * 20 + c);
+            } else if (part == 1) {
+                v = *reinterpret_cast<const float2*>(a.tb + (size_t)a.idxB[e] * a.strideB + c);
+            } else {
+                v = *reinterpret_cast<const float2*>(a.tc + (size_t)a.idxC[e] * a.strideC + c);
+                if (a.idxC2) {
+                    const float2 v2 = *reinterpret_cast<const float2*>(a.tc + (size_t)a.idxC2[e] * a.strideC + c);
+                    v.x += v2.x; v.y += v2.y;
+                }
             }
-            if (a.idxC2) {
-                const float2* p3 = reinterpret_cast<const float2*>(a.tc + (size_t)a.idxC2[e] * a.strideC);
-#pragma unroll
-                for (int c = 0; c < 10; ++c) { float2 v = p3[c]; x[40 + 2 * c] += v.x; x[41 + 2 * c] += v.y; }
-            }
+            attr[m * 61 + part * 20 + c] = v.x;
+            attr[m * 61 + part * 20 + c + 1] = v.y;
         }
+        asm volatile("bar.sync 1, 256;" ::: "memory");               // workers only (control warp is busy with TMA)
+        float x[60];
+#pragma unroll
+        for (int c = 0; c < 60; ++c) x[c] = attr[row * 61 + c];
+        tc_mbar_wait(&w_full, 0);
+        TC_STAMP(2);
         // A operand, K-major core-matrix layout: element (row, k) at  (k/4)*2048 + (row/8)*128 + (row%8)*16 + (k%4)*4 bytes
         const int row_off = (row >> 3) * 32 + (row & 7) * 4;       // in floats
 #pragma unroll 1
@@ -193,8 +209,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
             *reinterpret_cast<float4*>(a_lo + kc * 512 + row_off) = lo;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy (MMA) reads
+        TC_STAMP(3);
     }
     __syncthreads();
+    TC_STAMP(4);
 
     if (tid == TC_WORKERS) {
         // ================= TMA producer + MMA issuer (single thread) =================
@@ -242,17 +260,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
         for (int c = 0; c < nchunks; ++c) {
             const int s = c & 1, u = c >> 1;
             tc_mbar_wait(&t_full[s], u & 1);
+            if (c < 3) TC_STAMP(5 + 2 * c);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-            for (int q = 2 * colhalf; q < 2 * colhalf + 2; ++q) {
-                float v[32];
-                tc_tmem_ld32(lane_base + (uint32_t)(s * TC_BN + q * 32), v);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float v[2][32];
+            tc_tmem_ld32(lane_base + (uint32_t)(s * TC_BN + (2 * colhalf) * 32), v[0]);
+            tc_tmem_ld32(lane_base + (uint32_t)(s * TC_BN + (2 * colhalf + 1) * 32), v[1]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int qq = 0; qq < 2; ++qq) {
+                const int q = 2 * colhalf + qq;
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        make_float4(v[qq][4 * j], v[qq][4 * j + 1], v[qq][4 * j + 2], v[qq][4 * j + 3]);
                 __syncwarp();
                 const int n0 = c * TC_BN + q * 32 + c4 * 4;
                 if (n0 < W) {
@@ -266,11 +287,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            tc_mbar_arrive(&t_empty[s]);
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(&t_empty[s]);
+            if (c < 3) TC_STAMP(6 + 2 * c);
         }
+        TC_STAMP(11);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    TC_STAMP(12);
     if (warp == 8) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
     }
