@@ -96,9 +96,82 @@ __device__ __forceinline__ float tc_tf32_rna(float x) {
 __device__ long long* g_tc_dbg = nullptr;     // profiling aid: per-phase clock64() stamps of CTA 200 (tools/tc_phase_probe.py)
 #define TC_STAMP(i) do { if (g_tc_dbg && blockIdx.x == 200 && (tid & 127) == 0) g_tc_dbg[(tid >> 7) * 16 + (i)] = clock64(); } while (0)
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// pass 1: hidden activations h = ReLU(W1 . attr + b1) for every edge, written as the shared-memory image of the
+// tensor-core A operand (per 128-edge tile: [k/4][row/8][row%8][k%4], k = 60 carries the constant 1 that multiplies the
+// bias row of W2aug, k = 61..63 zero).  256 B per edge (3-10 % of the per-edge weight stream); keeps the gather and
+// the CUDA-core layer out of the tensor-core kernel, whose shared memory is full and cannot overlap them.
+// ---------------------------------------------------------------------------------------------------------------
+#define EH_THREADS 128
+__global__ void __launch_bounds__(EH_THREADS) edge_hidden_kernel(EdgeMlpArgs a, float* __restrict__ himg) {
+    __shared__ __align__(16) float w1s[3600];
+    __shared__ float b1s[64];
+    __shared__ float attr[128 * 61];
+    const int tid = threadIdx.x;
+    const int E = a.n_edges_dev ? *a.n_edges_dev : a.n_edges;
+    const int e0 = blockIdx.x * 128;
+    if (e0 >= E) return;
+    for (int i = tid; i < 3600; i += EH_THREADS) w1s[i] = a.w1[i];
+    if (tid < 60) b1s[tid] = a.b1[tid];
+    {
+        constexpr int NT = 128 * 30 / EH_THREADS;                    // 30 float2 items per thread, coalesced by part
+#pragma unroll 6
+        for (int t = 0; t < NT; ++t) {
+            const int i = tid + EH_THREADS * t, m = i / 30, q = i % 30, part = q / 10, c = (q % 10) * 2;
+            const int e = min(e0 + m, E - 1);
+            float2 v;
+            if (part == 0) {
+                const int r = a.perm ? a.perm[e] : e;
+                v = *reinterpret_cast<const float2*>(a.emb + (size_t)r * 20 + c);
+            } else if (part == 1) {
+                v = *reinterpret_cast<const float2*>(a.tb + (size_t)a.idxB[e] * a.strideB + c);
+            } else {
+                v = *reinterpret_cast<const float2*>(a.tc + (size_t)a.idxC[e] * a.strideC + c);
+                if (a.idxC2) {
+                    const float2 v2 = *reinterpret_cast<const float2*>(a.tc + (size_t)a.idxC2[e] * a.strideC + c);
+                    v.x += v2.x; v.y += v2.y;
+                }
+            }
+            attr[m * 61 + 2 * q] = v.x;
+            attr[m * 61 + 2 * q + 1] = v.y;
+        }
+    }
+    __syncthreads();
+    float x[60];
+#pragma unroll
+    for (int c = 0; c < 60; ++c) x[c] = attr[tid * 61 + c];
+    float* tile = himg + (size_t)blockIdx.x * (128 * TC_K) + (tid >> 3) * 32 + (tid & 7) * 4;
+#pragma unroll 1
+    for (int kc = 0; kc < 16; ++kc) {
+        float h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = kc * 4 + j;
+            float s = 0.f;
+            if (k < 60) {
+                s = b1s[k];
+                const float4* wr = reinterpret_cast<const float4*>(w1s + k * 60);
+#pragma unroll
+                for (int c = 0; c < 15; ++c) {
+                    const float4 wv = wr[c];
+                    s = fmaf(x[4 * c], wv.x, s); s = fmaf(x[4 * c + 1], wv.y, s);
+                    s = fmaf(x[4 * c + 2], wv.z, s); s = fmaf(x[4 * c + 3], wv.w, s);
+                }
+                s = fmaxf(s, 0.f);
+            } else if (k == 60) {
+                s = 1.0f;
+            }
+            h[j] = s;
+        }
+        *reinterpret_cast<float4*>(tile + kc * 512) = make_float4(h[0], h[1], h[2], h[3]);
+    }
+}
+
 struct EdgeMlpTcArgs {
     EdgeMlpArgs base;        // w2t unused here
     const float* w2img;      // [nchunks][2 (hi, lo)][16 k-chunks][16 row groups][8 rows][4] fp32, zero padded
+    float* himg;             // scratch: [ceil(E/128)][16][16][8][4] hidden activations (edge_hidden_kernel)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArgs args) {
@@ -107,9 +180,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
     float* a_hi = reinterpret_cast<float*>(tc_smem_raw);
     float* a_lo = a_hi + 128 * TC_K;
     float* b_st = a_lo + 128 * TC_K;                       // 2 stages x (hi 32 KB | lo 32 KB)
-    float* w1s = b_st + 2 * 2 * 128 * TC_K;                // [60][60] during setup; 8 x [32][32] transpose tiles afterwards
-    float* stg_all = w1s;
-    float* b1s = w1s + 8 * 32 * 32;                        // [64]
+    float* stg_all = b_st + 2 * 2 * 128 * TC_K;            // 8 x [32][32] transpose tiles
+    float* b1s = stg_all + 8 * 32 * 32;                    // (64 floats of padding before the barriers)
     uint64_t* bars = reinterpret_cast<uint64_t*>(b1s + 64);   // b_full[2], b_empty[2], t_full[2], t_empty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);      // bars[8]; bars[9] = first-layer weights barrier
     uint64_t *b_full = bars, *b_empty = bars + 2, *t_full = bars + 4, *t_empty = bars + 6;
@@ -140,73 +212,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
     const uint32_t tmem_base = *tmem_slot;
     TC_STAMP(1);
 
-    // control thread starts streaming the first weight chunk while the workers build the A operand
+    // control thread: A image of this tile (32 KB, written by edge_hidden_kernel) and the first weight chunk
     if (tid == TC_WORKERS) {
-        tc_mbar_expect_tx(&w_full, 3600 * 4 + 60 * 4);
-        tc_bulk_load(w1s, a.w1, 3600 * 4, &w_full);
-        tc_bulk_load(b1s, a.b1, 60 * 4, &w_full);
+        tc_mbar_expect_tx(&w_full, TC_OPER_BYTES);
+        tc_bulk_load(a_hi, args.himg + (size_t)blockIdx.x * (128 * TC_K), TC_OPER_BYTES, &w_full);
         tc_mbar_expect_tx(&b_full[0], 2 * TC_OPER_BYTES);
         tc_bulk_load(b_st, args.w2img, 2 * TC_OPER_BYTES, &b_full[0]);
     }
-    const int row = tid & 127, half = tid >> 7;
     if (warp < 8) {
-        // ---- gather the edge attributes and run half of the first layer (k in [32*half, 32*half+32)) on CUDA cores
-        // cooperative, coalesced gather of the 128 x 60 attribute tile into shared memory (aliases weight stage 1,
-        // idle until the main loop): 10 lanes fetch one 80-byte part as float2 -> a warp instruction touches ~4 lines
-        float* attr = b_st + 2 * 128 * TC_K;                         // [128][61]
-        for (int i = tid; i < 128 * 30; i += TC_WORKERS) {
-            const int m = i / 30, q = i % 30, part = q / 10, c = (q % 10) * 2;
-            const int e = min(e0 + m, E - 1);
-            float2 v;
-            if (part == 0) {
-                const int r = a.perm ? a.perm[e] : e;
-                v = *reinterpret_cast<const float2*>(a.emb + (size_t)r * 20 + c);
-            } else if (part == 1) {
-                v = *reinterpret_cast<const float2*>(a.tb + (size_t)a.idxB[e] * a.strideB + c);
-            } else {
-                v = *reinterpret_cast<const float2*>(a.tc + (size_t)a.idxC[e] * a.strideC + c);
-                if (a.idxC2) {
-                    const float2 v2 = *reinterpret_cast<const float2*>(a.tc + (size_t)a.idxC2[e] * a.strideC + c);
-                    v.x += v2.x; v.y += v2.y;
-                }
-            }
-            attr[m * 61 + part * 20 + c] = v.x;
-            attr[m * 61 + part * 20 + c + 1] = v.y;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");               // workers only (control warp is busy with TMA)
-        float x[60];
-#pragma unroll
-        for (int c = 0; c < 60; ++c) x[c] = attr[row * 61 + c];
+        // split the fp32 activations into tf32 hi + remainder lo, in place (3xTF32)
         tc_mbar_wait(&w_full, 0);
         TC_STAMP(2);
-        // A operand, K-major core-matrix layout: element (row, k) at  (k/4)*2048 + (row/8)*128 + (row%8)*16 + (k%4)*4 bytes
-        const int row_off = (row >> 3) * 32 + (row & 7) * 4;       // in floats
-#pragma unroll 1
-        for (int kc = 8 * half; kc < 8 * half + 8; ++kc) {
-            float h[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = kc * 4 + j;
-                float s = 0.f;
-                if (k < 60) {
-                    s = b1s[k];
-                    const float4* wr = reinterpret_cast<const float4*>(w1s + k * 60);
-#pragma unroll
-                    for (int c = 0; c < 15; ++c) {
-                        const float4 wv = wr[c];
-                        s = fmaf(x[4 * c], wv.x, s); s = fmaf(x[4 * c + 1], wv.y, s);
-                        s = fmaf(x[4 * c + 2], wv.z, s); s = fmaf(x[4 * c + 3], wv.w, s);
-                    }
-                    s = fmaxf(s, 0.f);
-                } else if (k == 60) {
-                    s = 1.0f;                                   // bias row of W2aug
-                }
-                h[j] = s;
-            }
-            float4 hi = make_float4(tc_tf32_rna(h[0]), tc_tf32_rna(h[1]), tc_tf32_rna(h[2]), tc_tf32_rna(h[3]));
-            float4 lo = make_float4(h[0] - hi.x, h[1] - hi.y, h[2] - hi.z, h[3] - hi.w);
-            *reinterpret_cast<float4*>(a_hi + kc * 512 + row_off) = hi;
-            *reinterpret_cast<float4*>(a_lo + kc * 512 + row_off) = lo;
+        for (int t = 0; t < (128 * TC_K / 4) / TC_WORKERS; ++t) {
+            const int i = (tid + TC_WORKERS * t) * 4;
+            const float4 h = *reinterpret_cast<const float4*>(a_hi + i);
+            const float4 hi = make_float4(tc_tf32_rna(h.x), tc_tf32_rna(h.y), tc_tf32_rna(h.z), tc_tf32_rna(h.w));
+            *reinterpret_cast<float4*>(a_hi + i) = hi;
+            *reinterpret_cast<float4*>(a_lo + i) = make_float4(h.x - hi.x, h.y - hi.y, h.z - hi.z, h.w - hi.w);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy (MMA) reads
         TC_STAMP(3);
@@ -304,7 +327,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
 static int edge_mlp_tc_launch(const EdgeMlpTcArgs& t, cudaStream_t st) {
     const EdgeMlpArgs& a = t.base;
     if (a.n_edges <= 0) return DP_OK;
-    if (a.in_dim != 60 || a.hid != 60 || (a.W % 4) != 0 || t.w2img == nullptr || a.tc == nullptr) {
+    if (a.in_dim != 60 || a.hid != 60 || (a.W % 4) != 0 || t.w2img == nullptr || a.tc == nullptr || t.himg == nullptr) {
         dp_set_error("dp_edge_mlp_tc: unsupported shape in=%d hid=%d W=%d", a.in_dim, a.hid, a.W);
         return DP_ERR_ARG;
     }
@@ -314,6 +337,7 @@ static int edge_mlp_tc_launch(const EdgeMlpTcArgs& t, cudaStream_t st) {
         attr_set = true;
     }
     dim3 grid((a.n_edges + 127) / 128);
+    edge_hidden_kernel<<<grid, EH_THREADS, 0, st>>>(a, t.himg);
     edge_mlp_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(t);
     return dp_check_launch("edge_mlp_tc");
 }

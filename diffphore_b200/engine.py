@@ -370,6 +370,8 @@ class Workspace:
         self.tr, self.rot, self.tor = f(b.B, 3), f(b.B, 3), f(max(b.n_rot, 1))
         w_elems = max(b.ll_cap * 2200, b.n_cross * 2200, b.n_pp * 1600, b.tor_cap * 1600, b.n_lig * 200, 1)
         self.w_elems = w_elems
+        max_edges = max(b.ll_cap, b.n_cross, b.n_pp, b.tor_cap, 1)
+        self.hbuf = f(((max_edges + 127) // 128) * 128 * 64)          # hidden activations of dp_edge_mlp_tc (pass 1 -> pass 2)
         self.wbuf = wbuf if wbuf is not None and wbuf.numel() >= w_elems else f(w_elems)   # per-edge TP weights
         self.n_launches = 0
 
@@ -412,7 +414,7 @@ class Engine:
         if self.use_tc and cw.w2img is not None:
             L.check(self.lib.dp_edge_mlp_tc(p(emb), p(perm), p(tb), p(idxB), tb.shape[1], p(tc), p(idxC), p(idxC2), tc.shape[1],
                                             p(cw.w1), p(cw.b1), p(cw.w2img), cw.in_dim, cw.hid, cw.W, p(n_dev), n_cap,
-                                            p(ws.wbuf), st), 'dp_edge_mlp_tc')
+                                            p(ws.hbuf), p(ws.wbuf), st), 'dp_edge_mlp_tc')
         else:
             L.check(self.lib.dp_edge_mlp(p(emb), p(perm), p(tb), p(idxB), tb.shape[1], p(tc), p(idxC), p(idxC2),
                                          tc.shape[1] if tc is not None else 0, p(cw.w1), p(cw.b1), p(cw.w2t), cw.in_dim,

@@ -234,11 +234,12 @@ def test_edge_mlp_tensor_core_path_matches_ffma_path(built_lib, W, E):
     img = _make_w2img(w3, b3).to(dev)
     n_dev = torch.tensor([E], dtype=torch.int32, device=dev)
     out_f, out_t = torch.zeros(E + 5, W, device=dev), torch.full((E + 5, W), 7.0, device=dev)
+    hbuf = torch.empty(((E + 200 + 127) // 128) * 128 * 64, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     built_lib.check(lib.dp_edge_mlp(p(emb), None, p(nb), p(ib), 50, p(nc), p(ic), None, 80, p(w1), p(b1), p(w2t), 60, 60, W,
                                     p(n_dev), E + 200, p(out_f), st))
     built_lib.check(lib.dp_edge_mlp_tc(p(emb), None, p(nb), p(ib), 50, p(nc), p(ic), None, 80, p(w1), p(b1), p(img), 60, 60, W,
-                                       p(n_dev), E + 200, p(out_t), st))
+                                       p(n_dev), E + 200, p(hbuf), p(out_t), st))
     torch.cuda.synchronize()
     attr = torch.cat([emb, nb[ib.long(), :20], nc[ic.long(), :20]], 1).double()
     ref = torch.relu(attr @ w1.double().T + b1.double()) @ w3.double().to(dev).T + b3.double().to(dev)

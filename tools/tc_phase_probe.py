@@ -15,20 +15,21 @@ for W in (600, 2200):
     w1, b1 = torch.randn(60, 60).to(dev), torch.randn(60).to(dev)
     img = _make_w2img(torch.randn(W, 60), torch.randn(W)).to(dev)
     out = torch.empty(E, W, device=dev)
+    hbuf = torch.empty(E * 64, device=dev)
     dbg = torch.zeros(64, dtype=torch.int64, device=dev)
     raw.dp_debug_set_tc_probe(ctypes.c_void_p(dbg.data_ptr()))
     st = torch.cuda.current_stream().cuda_stream
     for _ in range(3):
-        L.check(lib.dp_edge_mlp_tc(p(emb), None, p(nodes), p(ib), 100, p(nodes), p(ic), None, 100, p(w1), p(b1), p(img), 60, 60, W, None, E, p(out), st))
+        L.check(lib.dp_edge_mlp_tc(p(emb), None, p(nodes), p(ib), 100, p(nodes), p(ic), None, 100, p(w1), p(b1), p(img), 60, 60, W, None, E, p(hbuf), p(out), st))
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    L.check(lib.dp_edge_mlp_tc(p(emb), None, p(nodes), p(ib), 100, p(nodes), p(ic), None, 100, p(w1), p(b1), p(img), 60, 60, W, None, E, p(out), st))
+    L.check(lib.dp_edge_mlp_tc(p(emb), None, p(nodes), p(ib), 100, p(nodes), p(ic), None, 100, p(w1), p(b1), p(img), 60, 60, W, None, E, p(hbuf), p(out), st))
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     d = dbg.cpu().tolist()
     for half in (0, 1, 2):
-        t = d[half * 16:half * 16 + 13]
+        t = d[half * 16:half * 16 + 16]
         print(f'W={W} half={half} stamps (cycles since start):', [x - d[0] if x else None for x in t])
     print(f'W={W}: {ms:.3f} ms, {E * W * 4 / ms / 1e6:.0f} GB/s write, tiles/SM={E // 128 // 148}')
     raw.dp_debug_set_tc_probe(ctypes.c_void_p(0))
