@@ -134,6 +134,18 @@ int dp_edge_mlp_tc(const float* emb, const int32_t* perm, const float* tb, const
     return edge_mlp_tc_launch(t, ST(stream));
 }
 
+/* profiling aid (not part of the public header): pass 1 of dp_edge_mlp_tc alone */
+int dp_debug_edge_hidden(const float* emb, const float* tb, const int32_t* idxB, int32_t strideB, const float* tc,
+                         const int32_t* idxC, int32_t strideC, const float* w1, const float* b1, int32_t n_edges,
+                         float* h_scratch, void* stream) {
+    EdgeMlpArgs a;
+    a.emb = emb; a.perm = nullptr; a.tb = tb; a.idxB = idxB; a.strideB = strideB; a.tc = tc; a.idxC = idxC; a.idxC2 = nullptr;
+    a.strideC = strideC; a.w1 = w1; a.b1 = b1; a.w2t = nullptr; a.in_dim = 60; a.hid = 60; a.W = 0;
+    a.n_edges_dev = nullptr; a.n_edges = n_edges; a.out = nullptr;
+    edge_hidden_kernel<<<min((n_edges + 127) / 128, 148 * 4), EH_THREADS, 0, ST(stream)>>>(a, h_scratch);
+    return dp_check_launch("edge_hidden");
+}
+
 /* profiling aid (not part of the public header): route per-phase clock stamps of dp_edge_mlp_tc to a device buffer */
 int dp_debug_set_tc_probe(long long* buf) {
     cudaError_t e = cudaMemcpyToSymbol(g_tc_dbg, &buf, sizeof(buf));

@@ -10,6 +10,7 @@
 // With 3 x 8 MMAs per chunk the tensor pipe needs ~1.6k clk per 128x128 chunk while the 64 KB of output need
 // ~4k clk of this SM's share of HBM write bandwidth: the kernel is HBM-write-bound by design.
 #pragma once
+#include <cuda.h>
 #include "common.cuh"
 #include "edge_mlp.cuh"
 
@@ -110,61 +111,67 @@ __global__ void __launch_bounds__(EH_THREADS) edge_hidden_kernel(EdgeMlpArgs a, 
     __shared__ float attr[128 * 61];
     const int tid = threadIdx.x;
     const int E = a.n_edges_dev ? *a.n_edges_dev : a.n_edges;
-    const int e0 = blockIdx.x * 128;
-    if (e0 >= E) return;
-    for (int i = tid; i < 3600; i += EH_THREADS) w1s[i] = a.w1[i];
+    const int ntiles = (E + 127) / 128;
+    if ((int)blockIdx.x >= ntiles) return;
+#pragma unroll 4
+    for (int i = tid; i < 900; i += EH_THREADS)
+        reinterpret_cast<float4*>(w1s)[i] = __ldg(reinterpret_cast<const float4*>(a.w1) + i);
     if (tid < 60) b1s[tid] = a.b1[tid];
-    {
-        constexpr int NT = 128 * 30 / EH_THREADS;                    // 30 float2 items per thread, coalesced by part
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {          // persistent: W1 is staged once per CTA
+        const int e0 = tile * 128;
+        __syncthreads();                                                     // attr of the previous tile fully consumed
+        {
+            constexpr int NT = 128 * 30 / EH_THREADS;                        // 30 float2 items per thread, coalesced by part
 #pragma unroll 6
-        for (int t = 0; t < NT; ++t) {
-            const int i = tid + EH_THREADS * t, m = i / 30, q = i % 30, part = q / 10, c = (q % 10) * 2;
-            const int e = min(e0 + m, E - 1);
-            float2 v;
-            if (part == 0) {
-                const int r = a.perm ? a.perm[e] : e;
-                v = *reinterpret_cast<const float2*>(a.emb + (size_t)r * 20 + c);
-            } else if (part == 1) {
-                v = *reinterpret_cast<const float2*>(a.tb + (size_t)a.idxB[e] * a.strideB + c);
-            } else {
-                v = *reinterpret_cast<const float2*>(a.tc + (size_t)a.idxC[e] * a.strideC + c);
-                if (a.idxC2) {
-                    const float2 v2 = *reinterpret_cast<const float2*>(a.tc + (size_t)a.idxC2[e] * a.strideC + c);
-                    v.x += v2.x; v.y += v2.y;
+            for (int t = 0; t < NT; ++t) {
+                const int i = tid + EH_THREADS * t, m = i / 30, q = i % 30, part = q / 10, c = (q % 10) * 2;
+                const int e = min(e0 + m, E - 1);
+                float2 v;
+                if (part == 0) {
+                    const int r = a.perm ? a.perm[e] : e;
+                    v = *reinterpret_cast<const float2*>(a.emb + (size_t)r * 20 + c);
+                } else if (part == 1) {
+                    v = *reinterpret_cast<const float2*>(a.tb + (size_t)a.idxB[e] * a.strideB + c);
+                } else {
+                    v = *reinterpret_cast<const float2*>(a.tc + (size_t)a.idxC[e] * a.strideC + c);
+                    if (a.idxC2) {
+                        const float2 v2 = *reinterpret_cast<const float2*>(a.tc + (size_t)a.idxC2[e] * a.strideC + c);
+                        v.x += v2.x; v.y += v2.y;
+                    }
                 }
+                attr[m * 61 + 2 * q] = v.x;
+                attr[m * 61 + 2 * q + 1] = v.y;
             }
-            attr[m * 61 + 2 * q] = v.x;
-            attr[m * 61 + 2 * q + 1] = v.y;
         }
-    }
-    __syncthreads();
-    float x[60];
+        __syncthreads();
+        float x[60];
 #pragma unroll
-    for (int c = 0; c < 60; ++c) x[c] = attr[tid * 61 + c];
-    float* tile = himg + (size_t)blockIdx.x * (128 * TC_K) + (tid >> 3) * 32 + (tid & 7) * 4;
+        for (int c = 0; c < 60; ++c) x[c] = attr[tid * 61 + c];
+        float* out_tile = himg + (size_t)tile * (128 * TC_K) + (tid >> 3) * 32 + (tid & 7) * 4;
 #pragma unroll 1
-    for (int kc = 0; kc < 16; ++kc) {
-        float h[4];
+        for (int kc = 0; kc < 16; kc += 2) {                                 // 8 independent accumulation chains
+            float h[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int k = kc * 4 + j;
-            float s = 0.f;
-            if (k < 60) {
-                s = b1s[k];
-                const float4* wr = reinterpret_cast<const float4*>(w1s + k * 60);
+            for (int j = 0; j < 8; ++j) h[j] = (kc * 4 + j < 60) ? b1s[kc * 4 + j] : 0.f;
 #pragma unroll
-                for (int c = 0; c < 15; ++c) {
-                    const float4 wv = wr[c];
-                    s = fmaf(x[4 * c], wv.x, s); s = fmaf(x[4 * c + 1], wv.y, s);
-                    s = fmaf(x[4 * c + 2], wv.z, s); s = fmaf(x[4 * c + 3], wv.w, s);
+            for (int c = 0; c < 15; ++c) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (kc * 4 + j < 60) {
+                        const float4 wv = *reinterpret_cast<const float4*>(w1s + (kc * 4 + j) * 60 + 4 * c);
+                        h[j] = fmaf(x[4 * c], wv.x, h[j]); h[j] = fmaf(x[4 * c + 1], wv.y, h[j]);
+                        h[j] = fmaf(x[4 * c + 2], wv.z, h[j]); h[j] = fmaf(x[4 * c + 3], wv.w, h[j]);
+                    }
                 }
-                s = fmaxf(s, 0.f);
-            } else if (k == 60) {
-                s = 1.0f;
             }
-            h[j] = s;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = kc * 4 + j;
+                h[j] = k < 60 ? fmaxf(h[j], 0.f) : (k == 60 ? 1.0f : 0.f);
+            }
+            *reinterpret_cast<float4*>(out_tile + kc * 512) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(out_tile + (kc + 1) * 512) = make_float4(h[4], h[5], h[6], h[7]);
         }
-        *reinterpret_cast<float4*>(tile + kc * 512) = make_float4(h[0], h[1], h[2], h[3]);
     }
 }
 
@@ -174,8 +181,8 @@ struct EdgeMlpTcArgs {
     float* himg;             // scratch: [ceil(E/128)][16][16][8][4] hidden activations (edge_hidden_kernel)
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArgs args) {
-    extern __shared__ __align__(128) uint8_t tc_smem_raw[];
+__global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArgs args, const __grid_constant__ CUtensorMap out_map) {
+    extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
     const EdgeMlpArgs& a = args.base;
     float* a_hi = reinterpret_cast<float*>(tc_smem_raw);
     float* a_lo = a_hi + 128 * TC_K;
@@ -279,7 +286,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
         float* stg = stg_all + warp * 32 * 32;
         const int wq = warp & 3, colhalf = warp >> 2;
         const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
-        const int r_sub = lane >> 3, c4 = lane & 7;
         for (int c = 0; c < nchunks; ++c) {
             const int s = c & 1, u = c >> 1;
             tc_mbar_wait(&t_full[s], u & 1);
@@ -292,21 +298,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
 #pragma unroll
             for (int qq = 0; qq < 2; ++qq) {
                 const int q = 2 * colhalf + qq;
+                // the previous TMA store must have finished READING this warp's tile before it is overwritten
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
                         make_float4(v[qq][4 * j], v[qq][4 * j + 1], v[qq][4 * j + 2], v[qq][4 * j + 3]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                const int n0 = c * TC_BN + q * 32 + c4 * 4;
-                if (n0 < W) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = 4 * i + r_sub;
-                        const int e = e0 + wq * 32 + r;
-                        const float4 o = *reinterpret_cast<const float4*>(stg + r * 32 + ((c4 ^ (r & 7)) << 2));
-                        if (e < E) *reinterpret_cast<float4*>(a.out + (size_t)e * W + n0) = o;
-                    }
+                const int n0 = c * TC_BN + q * 32;
+                if (lane == 0 && n0 < W) {
+                    // 32 x 32 fp32 box, 128-byte swizzle (== the XOR pattern above); rows/columns beyond the tensor are clipped
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&out_map),
+                                 "r"(n0), "r"(e0 + wq * 32), "r"(tc_smem(stg))
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -314,6 +321,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
             if (lane == 0) tc_mbar_arrive(&t_empty[s]);
             if (c < 3) TC_STAMP(6 + 2 * c);
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         TC_STAMP(11);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -336,8 +344,38 @@ static int edge_mlp_tc_launch(const EdgeMlpTcArgs& t, cudaStream_t st) {
         cudaFuncSetAttribute(edge_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
         attr_set = true;
     }
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+            dp_set_error("dp_edge_mlp_tc: cuTensorMapEncodeTiled is not available");
+            return DP_ERR_CUDA;
+        }
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    CUtensorMap map;
+    const cuuint64_t gdim[2] = {(cuuint64_t)a.W, (cuuint64_t)a.n_edges};
+    const cuuint64_t gstride[1] = {(cuuint64_t)a.W * 4};
+    const cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+    const CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.out, gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        dp_set_error("dp_edge_mlp_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return DP_ERR_CUDA;
+    }
     dim3 grid((a.n_edges + 127) / 128);
-    edge_hidden_kernel<<<grid, EH_THREADS, 0, st>>>(a, t.himg);
-    edge_mlp_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(t);
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    }
+    edge_hidden_kernel<<<dim3(min((int)grid.x, n_sm * 4)), EH_THREADS, 0, st>>>(a, t.himg);
+    edge_mlp_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(t, map);
     return dp_check_launch("edge_mlp_tc");
 }

@@ -33,6 +33,12 @@ for W in (600, 2200):
         print(f'W={W} half={half} stamps (cycles since start):', [x - d[0] if x else None for x in t])
     print(f'W={W}: {ms:.3f} ms, {E * W * 4 / ms / 1e6:.0f} GB/s write, tiles/SM={E // 128 // 148}')
     raw.dp_debug_set_tc_probe(ctypes.c_void_p(0))
+    V = ctypes.c_void_p
+    e0.record()
+    raw.dp_debug_edge_hidden(V(emb.data_ptr()), V(nodes.data_ptr()), V(ib.data_ptr()), 100, V(nodes.data_ptr()), V(ic.data_ptr()), 100,
+                             V(w1.data_ptr()), V(b1.data_ptr()), E, V(hbuf.data_ptr()), V(st))
+    e1.record(); torch.cuda.synchronize()
+    print(f'   pass 1 (hidden) alone: {e0.elapsed_time(e1):.3f} ms for {E} edges')
 buf = torch.empty(2 << 30, dtype=torch.float32, device=dev)
 for _ in range(2):
     buf.fill_(1.0)
