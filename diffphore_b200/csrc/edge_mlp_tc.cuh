@@ -104,109 +104,127 @@ __device__ long long* g_tc_dbg = nullptr;     // profiling aid: per-phase clock6
 // bias row of W2aug, k = 61..63 zero).  256 B per edge (3-10 % of the per-edge weight stream); keeps the gather and
 // the CUDA-core layer out of the tensor-core kernel, whose shared memory is full and cannot overlap them.
 // ---------------------------------------------------------------------------------------------------------------
-#define EH_THREADS 128
+#define EH_THREADS 256
+#define EH_LD 132                   // padded row length of the transposed attribute tile
 __global__ void __launch_bounds__(EH_THREADS) edge_hidden_kernel(EdgeMlpArgs a, float* __restrict__ himg) {
-    __shared__ __align__(16) float w1s[3600];
-    __shared__ float b1s[64];
-    __shared__ float attr[128 * 61];
+    // register-tiled SGEMM  h[128 edges, 64] = attr[128, 60] . W1T[60, 64]: a thread owns 4 edges x 8 outputs, per k it
+    // reads 4 attributes (one float4 of the k-major tile) and 8 weights (two broadcast float4) for 32 FMAs.
+    __shared__ __align__(16) float w1t[60 * 64];          // [k][o], o >= 60 zero
+    __shared__ __align__(16) float attrT[60 * EH_LD];     // [c][m]
     const int tid = threadIdx.x;
     const int E = a.n_edges_dev ? *a.n_edges_dev : a.n_edges;
     const int ntiles = (E + 127) / 128;
     if ((int)blockIdx.x >= ntiles) return;
-#pragma unroll 4
-    for (int i = tid; i < 900; i += EH_THREADS)
-        reinterpret_cast<float4*>(w1s)[i] = __ldg(reinterpret_cast<const float4*>(a.w1) + i);
-    if (tid < 60) b1s[tid] = a.b1[tid];
+    for (int i = tid; i < 60 * 64; i += EH_THREADS) {
+        const int k = i >> 6, o = i & 63;
+        w1t[i] = o < 60 ? a.w1[o * 60 + k] : 0.f;
+    }
+    const int mg = tid & 31, og = tid >> 5, m0 = 4 * mg, o0 = 8 * og;
+    float bias[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bias[j] = (o0 + j < 60) ? a.b1[o0 + j] : 0.f;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {          // persistent: W1 is staged once per CTA
         const int e0 = tile * 128;
-        __syncthreads();                                                     // attr of the previous tile fully consumed
+        __syncthreads();                                                     // previous tile fully consumed
         {
-            constexpr int NT = 128 * 30 / EH_THREADS;                        // 30 float2 items per thread, coalesced by part
-#pragma unroll 6
+            constexpr int NT = 128 * 30 / EH_THREADS;                        // 15 float2 items per thread, coalesced by part
+            int ridx[NT], ridx2[NT];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const int i = tid + EH_THREADS * t, m = i / 30, part = (i % 30) / 10;
+                const int e = min(e0 + m, E - 1);
+                ridx[t] = part == 0 ? (a.perm ? a.perm[e] : e) : (part == 1 ? a.idxB[e] : a.idxC[e]);
+                ridx2[t] = (part == 2 && a.idxC2) ? a.idxC2[e] : -1;
+            }
+#pragma unroll
             for (int t = 0; t < NT; ++t) {
                 const int i = tid + EH_THREADS * t, m = i / 30, q = i % 30, part = q / 10, c = (q % 10) * 2;
-                const int e = min(e0 + m, E - 1);
-                float2 v;
-                if (part == 0) {
-                    const int r = a.perm ? a.perm[e] : e;
-                    v = *reinterpret_cast<const float2*>(a.emb + (size_t)r * 20 + c);
-                } else if (part == 1) {
-                    v = *reinterpret_cast<const float2*>(a.tb + (size_t)a.idxB[e] * a.strideB + c);
-                } else {
-                    v = *reinterpret_cast<const float2*>(a.tc + (size_t)a.idxC[e] * a.strideC + c);
-                    if (a.idxC2) {
-                        const float2 v2 = *reinterpret_cast<const float2*>(a.tc + (size_t)a.idxC2[e] * a.strideC + c);
-                        v.x += v2.x; v.y += v2.y;
-                    }
+                const float* src = part == 0 ? a.emb + (size_t)ridx[t] * 20
+                                             : (part == 1 ? a.tb + (size_t)ridx[t] * a.strideB : a.tc + (size_t)ridx[t] * a.strideC);
+                float2 v = *reinterpret_cast<const float2*>(src + c);
+                if (ridx2[t] >= 0) {
+                    const float2 v2 = *reinterpret_cast<const float2*>(a.tc + (size_t)ridx2[t] * a.strideC + c);
+                    v.x += v2.x; v.y += v2.y;
                 }
-                attr[m * 61 + 2 * q] = v.x;
-                attr[m * 61 + 2 * q + 1] = v.y;
+                attrT[(2 * q) * EH_LD + m] = v.x;                            // part*20 + c == 2*q
+                attrT[(2 * q + 1) * EH_LD + m] = v.y;
             }
         }
         __syncthreads();
-        float x[60];
+        float h[4][8];
 #pragma unroll
-        for (int c = 0; c < 60; ++c) x[c] = attr[tid * 61 + c];
-        float* out_tile = himg + (size_t)tile * (128 * TC_K) + (tid >> 3) * 32 + (tid & 7) * 4;
-#pragma unroll 1
-        for (int kc = 0; kc < 16; kc += 2) {                                 // 8 independent accumulation chains
-            float h[8];
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) h[j] = (kc * 4 + j < 60) ? b1s[kc * 4 + j] : 0.f;
+            for (int j = 0; j < 8; ++j) h[i][j] = bias[j];
+#pragma unroll 4
+        for (int k = 0; k < 60; ++k) {
+            const float4 av = *reinterpret_cast<const float4*>(attrT + k * EH_LD + m0);
+            const float4 b0 = *reinterpret_cast<const float4*>(w1t + k * 64 + o0);
+            const float4 b1v = *reinterpret_cast<const float4*>(w1t + k * 64 + o0 + 4);
+            const float am[4] = {av.x, av.y, av.z, av.w};
+            const float bm[8] = {b0.x, b0.y, b0.z, b0.w, b1v.x, b1v.y, b1v.z, b1v.w};
 #pragma unroll
-            for (int c = 0; c < 15; ++c) {
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (kc * 4 + j < 60) {
-                        const float4 wv = *reinterpret_cast<const float4*>(w1s + (kc * 4 + j) * 60 + 4 * c);
-                        h[j] = fmaf(x[4 * c], wv.x, h[j]); h[j] = fmaf(x[4 * c + 1], wv.y, h[j]);
-                        h[j] = fmaf(x[4 * c + 2], wv.z, h[j]); h[j] = fmaf(x[4 * c + 3], wv.w, h[j]);
-                    }
-                }
-            }
+                for (int j = 0; j < 8; ++j) h[i][j] = fmaf(am[i], bm[j], h[i][j]);
+        }
+        // ReLU, constant-1 column (k = 60) and zero padding, then the tiled operand image [k/4][row/8][row%8][k%4]
+        float* out_tile = himg + (size_t)tile * (128 * TC_K) + (size_t)(2 * og) * 512 + m0 * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float r[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int k = kc * 4 + j;
-                h[j] = k < 60 ? fmaxf(h[j], 0.f) : (k == 60 ? 1.0f : 0.f);
+                const int o = o0 + j;
+                r[j] = o < 60 ? fmaxf(h[i][j], 0.f) : (o == 60 ? 1.0f : 0.f);
             }
-            *reinterpret_cast<float4*>(out_tile + kc * 512) = make_float4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<float4*>(out_tile + (kc + 1) * 512) = make_float4(h[4], h[5], h[6], h[7]);
+            // rows m0..m0+3 lie in one 8-row group (m0 is a multiple of 4): offset (m/8)*32 + (m%8)*4 == m*4
+            *reinterpret_cast<float4*>(out_tile + i * 4) = make_float4(r[0], r[1], r[2], r[3]);
+            *reinterpret_cast<float4*>(out_tile + 512 + i * 4) = make_float4(r[4], r[5], r[6], r[7]);
         }
     }
 }
 
 struct EdgeMlpTcArgs {
     EdgeMlpArgs base;        // w2t unused here
-    const float* w2img;      // [nchunks][2 (hi, lo)][16 k-chunks][16 row groups][8 rows][4] fp32, zero padded
+    const float* w2img;      // [ceil(W/64)][2 (hi, lo)][16 k-chunks][8 row groups][8 rows][4] fp32, zero padded
     float* himg;             // scratch: [ceil(E/128)][16][16][8][4] hidden activations (edge_hidden_kernel)
 };
+
+// ---------------------------------------------------------------------------------------------------------------
+// pass 2: w[256 edges, W] = h . W2aug on tcgen05.  One CTA owns TWO 128-edge tiles (A operands resident in shared
+// memory, hi/lo split = 128 KB) and streams the second-layer weights in 64-column half-chunks (32 KB, 2-stage TMA
+// ring): every weight byte fetched from L2 feeds 256 rows, which halves the L2->SM operand traffic that bounded the
+// one-tile version (it re-read 64 KB of weights for every 64 KB of output).  Per half-chunk: 2 x 24 MMAs
+// (M=128, N=64, K=8, kind::tf32; hi*hi + hi*lo + lo*hi) into 4 TMEM accumulator slots (2 stages x 2 tiles x 64 cols);
+// 8 epilogue warps drain one 32x32 block each per (half-chunk, tile): tcgen05.ld -> swizzled smem tile -> TMA store.
+// ---------------------------------------------------------------------------------------------------------------
+#define TC2_BN 64
+#define TC2_B_STAGE_BYTES (2 * TC2_BN * TC_K * 4)                 // hi + lo of a 64 x 64 fp32 block = 32 KB
+#define TC2_SMEM_BYTES (4 * TC_OPER_BYTES + 2 * TC2_B_STAGE_BYTES + 8 * 32 * 32 * 4 + 256)
 
 __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArgs args, const __grid_constant__ CUtensorMap out_map) {
     extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
     const EdgeMlpArgs& a = args.base;
-    float* a_hi = reinterpret_cast<float*>(tc_smem_raw);
-    float* a_lo = a_hi + 128 * TC_K;
-    float* b_st = a_lo + 128 * TC_K;                       // 2 stages x (hi 32 KB | lo 32 KB)
-    float* stg_all = b_st + 2 * 2 * 128 * TC_K;            // 8 x [32][32] transpose tiles
-    float* b1s = stg_all + 8 * 32 * 32;                    // (64 floats of padding before the barriers)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b1s + 64);   // b_full[2], b_empty[2], t_full[2], t_empty[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);      // bars[8]; bars[9] = first-layer weights barrier
-    uint64_t *b_full = bars, *b_empty = bars + 2, *t_full = bars + 4, *t_empty = bars + 6;
-    uint64_t& w_full = bars[9];
+    float* a_op = reinterpret_cast<float*>(tc_smem_raw);              // [tile][hi|lo][128 x 64]
+    float* b_st = a_op + 4 * 128 * TC_K;                              // 2 stages x (hi 16 KB | lo 16 KB)
+    float* stg_all = b_st + 2 * 2 * TC2_BN * TC_K;                    // 8 x [32][32] swizzled transpose tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stg_all + 8 * 32 * 32);
+    uint64_t *b_full = bars, *b_empty = bars + 2, *t_full = bars + 4 /*[stage][tile]*/, *t_empty = bars + 8, *a_full = bars + 12;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int E = a.n_edges_dev ? *a.n_edges_dev : a.n_edges;
-    const int e0 = blockIdx.x * 128;
+    const int e0 = blockIdx.x * 256;
     if (e0 >= E) return;
-    const int W = a.W, nchunks = (W + TC_BN - 1) / TC_BN;
+    const int ntile = (E - e0 > 128) ? 2 : 1;
+    const int W = a.W, nhc = (W + TC2_BN - 1) / TC2_BN;
 
     TC_STAMP(0);
     if (tid == 0) {
-        tc_mbar_init(&b_full[0], 1); tc_mbar_init(&b_full[1], 1);
-        tc_mbar_init(&b_empty[0], 1); tc_mbar_init(&b_empty[1], 1);
-        tc_mbar_init(&t_full[0], 1); tc_mbar_init(&t_full[1], 1);
-        tc_mbar_init(&w_full, 1);
-        tc_mbar_init(&t_empty[0], TC_WORKERS / 32); tc_mbar_init(&t_empty[1], TC_WORKERS / 32);
+        for (int i = 0; i < 2; ++i) { tc_mbar_init(&b_full[i], 1); tc_mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 4; ++i) { tc_mbar_init(&t_full[i], 1); tc_mbar_init(&t_empty[i], TC_WORKERS / 32); }
+        tc_mbar_init(a_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) {
@@ -219,24 +237,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
     const uint32_t tmem_base = *tmem_slot;
     TC_STAMP(1);
 
-    // control thread: A image of this tile (32 KB, written by edge_hidden_kernel) and the first weight chunk
     if (tid == TC_WORKERS) {
-        tc_mbar_expect_tx(&w_full, TC_OPER_BYTES);
-        tc_bulk_load(a_hi, args.himg + (size_t)blockIdx.x * (128 * TC_K), TC_OPER_BYTES, &w_full);
-        tc_mbar_expect_tx(&b_full[0], 2 * TC_OPER_BYTES);
-        tc_bulk_load(b_st, args.w2img, 2 * TC_OPER_BYTES, &b_full[0]);
+        // A images (fp32 hidden activations written by edge_hidden_kernel) land in the hi slots; first weight half-chunk
+        tc_mbar_expect_tx(a_full, ntile * TC_OPER_BYTES);
+        for (int i = 0; i < ntile; ++i)
+            tc_bulk_load(a_op + i * 2 * 128 * TC_K, args.himg + ((size_t)blockIdx.x * 2 + i) * (128 * TC_K), TC_OPER_BYTES, a_full);
+        tc_mbar_expect_tx(&b_full[0], TC2_B_STAGE_BYTES);
+        tc_bulk_load(b_st, args.w2img, TC2_B_STAGE_BYTES, &b_full[0]);
     }
     if (warp < 8) {
         // split the fp32 activations into tf32 hi + remainder lo, in place (3xTF32)
-        tc_mbar_wait(&w_full, 0);
+        tc_mbar_wait(a_full, 0);
         TC_STAMP(2);
+        for (int i = 0; i < ntile; ++i) {
+            float* hi_p = a_op + i * 2 * 128 * TC_K;
+            float* lo_p = hi_p + 128 * TC_K;
 #pragma unroll
-        for (int t = 0; t < (128 * TC_K / 4) / TC_WORKERS; ++t) {
-            const int i = (tid + TC_WORKERS * t) * 4;
-            const float4 h = *reinterpret_cast<const float4*>(a_hi + i);
-            const float4 hi = make_float4(tc_tf32_rna(h.x), tc_tf32_rna(h.y), tc_tf32_rna(h.z), tc_tf32_rna(h.w));
-            *reinterpret_cast<float4*>(a_hi + i) = hi;
-            *reinterpret_cast<float4*>(a_lo + i) = make_float4(h.x - hi.x, h.y - hi.y, h.z - hi.z, h.w - hi.w);
+            for (int t = 0; t < (128 * TC_K / 4) / TC_WORKERS; ++t) {
+                const int o = (tid + TC_WORKERS * t) * 4;
+                const float4 h = *reinterpret_cast<const float4*>(hi_p + o);
+                const float4 hi = make_float4(tc_tf32_rna(h.x), tc_tf32_rna(h.y), tc_tf32_rna(h.z), tc_tf32_rna(h.w));
+                *reinterpret_cast<float4*>(hi_p + o) = hi;
+                *reinterpret_cast<float4*>(lo_p + o) = make_float4(h.x - hi.x, h.y - hi.y, h.z - hi.z, h.w - hi.w);
+            }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy (MMA) reads
         TC_STAMP(3);
@@ -246,80 +269,77 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
 
     if (tid == TC_WORKERS) {
         // ================= TMA producer + MMA issuer (single thread) =================
-        // instruction descriptor: D=F32, A=B=TF32, K-major both, N=128, M=128
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        const uint32_t a_hi_s = tc_smem(a_hi), a_lo_s = tc_smem(a_lo);
-        for (int c = 0; c < nchunks; ++c) {
-            const int s = c & 1, u = c >> 1;
-            if (c + 1 < nchunks) {
-                const int s1 = (c + 1) & 1, u1 = (c + 1) >> 1;
+        // instruction descriptor: D=F32, A=B=TF32, K-major both, N=64, M=128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC2_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        for (int hc = 0; hc < nhc; ++hc) {
+            const int s = hc & 1, u = hc >> 1;
+            if (hc + 1 < nhc) {
+                const int s1 = (hc + 1) & 1, u1 = (hc + 1) >> 1;
                 tc_mbar_wait(&b_empty[s1], (u1 & 1) ^ 1);
-                tc_mbar_expect_tx(&b_full[s1], 2 * TC_OPER_BYTES);
-                tc_bulk_load(b_st + s1 * 2 * 128 * TC_K, args.w2img + (size_t)(c + 1) * 2 * 128 * TC_K, 2 * TC_OPER_BYTES,
+                tc_mbar_expect_tx(&b_full[s1], TC2_B_STAGE_BYTES);
+                tc_bulk_load(b_st + s1 * 2 * TC2_BN * TC_K, args.w2img + (size_t)(hc + 1) * 2 * TC2_BN * TC_K, TC2_B_STAGE_BYTES,
                              &b_full[s1]);
             }
             tc_mbar_wait(&b_full[s], u & 1);
-            tc_mbar_wait(&t_empty[s], (u & 1) ^ 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t b_hi_s = tc_smem(b_st + s * 2 * 128 * TC_K), b_lo_s = b_hi_s + TC_OPER_BYTES;
-            const uint32_t d = tmem_base + (uint32_t)(s * TC_BN);
+            const uint32_t b_hi_s = tc_smem(b_st + s * 2 * TC2_BN * TC_K), b_lo_s = b_hi_s + TC2_BN * TC_K * 4;
+            for (int i = 0; i < ntile; ++i) {
+                tc_mbar_wait(&t_empty[s * 2 + i], (u & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi_s = tc_smem(a_op + i * 2 * 128 * TC_K), a_lo_s = a_hi_s + TC_OPER_BYTES;
+                const uint32_t d = tmem_base + (uint32_t)((s * 2 + i) * TC2_BN);
 #pragma unroll
-            for (int combo = 0; combo < 3; ++combo) {
-                const uint32_t as = combo == 2 ? a_lo_s : a_hi_s;
-                const uint32_t bs = combo == 1 ? b_lo_s : b_hi_s;
+                for (int combo = 0; combo < 3; ++combo) {
+                    const uint32_t as = combo == 2 ? a_lo_s : a_hi_s;
+                    const uint32_t bs = combo == 1 ? b_lo_s : b_hi_s;
 #pragma unroll
-                for (int ks = 0; ks < TC_K / 8; ++ks) {
-                    const uint64_t ad = tc_smem_desc(as + ks * 2 * 2048, 2048, 128);
-                    const uint64_t bd = tc_smem_desc(bs + ks * 2 * 2048, 2048, 128);
-                    tc_mma_tf32(d, ad, bd, idesc, (combo | ks) ? 1u : 0u);
+                    for (int ks = 0; ks < TC_K / 8; ++ks) {
+                        const uint64_t ad = tc_smem_desc(as + ks * 2 * 2048, 2048, 128);      // 16 row groups per K chunk
+                        const uint64_t bd = tc_smem_desc(bs + ks * 2 * 1024, 1024, 128);      // 8 row groups per K chunk
+                        tc_mma_tf32(d, ad, bd, idesc, (combo | ks) ? 1u : 0u);
+                    }
                 }
+                tc_commit(&t_full[s * 2 + i]);    // accumulator slot complete
             }
-            tc_commit(&b_empty[s]);       // smem stage reusable once these MMAs have read it
-            tc_commit(&t_full[s]);        // accumulator stage complete
+            tc_commit(&b_empty[s]);               // weight stage reusable once all MMAs above have read it
         }
     } else if (warp < 8) {
-        // ================= epilogue: TMEM -> registers -> smem transpose -> coalesced HBM stores =================
-        // tcgen05.ld hands lane t the 32 columns of TMEM lane (row) 32*(warp%4)+t; a direct store would touch 32 lines
-        // per instruction, so each warp transposes its 32x32 block through a private XOR-swizzled tile and stores
-        // 4 rows x 128 contiguous bytes per instruction.  Warps 0-3 drain columns 0-63 of a chunk, warps 4-7 columns
-        // 64-127 (a warp may only touch the TMEM lane quarter warp%4).
+        // ================= epilogue: TMEM -> registers -> swizzled smem tile -> TMA tensor store =================
+        // warp w drains the 32x32 block (rows 32*(w%4).., columns 32*(w/4)..) of every (half-chunk, tile) accumulator.
         float* stg = stg_all + warp * 32 * 32;
-        const int wq = warp & 3, colhalf = warp >> 2;
+        const int wq = warp & 3, ch = warp >> 2;
         const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
-        for (int c = 0; c < nchunks; ++c) {
-            const int s = c & 1, u = c >> 1;
-            tc_mbar_wait(&t_full[s], u & 1);
-            if (c < 3) TC_STAMP(5 + 2 * c);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float v[2][32];
-            tc_tmem_ld32(lane_base + (uint32_t)(s * TC_BN + (2 * colhalf) * 32), v[0]);
-            tc_tmem_ld32(lane_base + (uint32_t)(s * TC_BN + (2 * colhalf + 1) * 32), v[1]);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int qq = 0; qq < 2; ++qq) {
-                const int q = 2 * colhalf + qq;
-                // the previous TMA store must have finished READING this warp's tile before it is overwritten
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        for (int hc = 0; hc < nhc; ++hc) {
+            const int s = hc & 1, u = hc >> 1;
+            for (int i = 0; i < ntile; ++i) {
+                tc_mbar_wait(&t_full[s * 2 + i], u & 1);
+                if (hc < 2 && i == 0) TC_STAMP(5 + 2 * hc);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                float v[32];
+                tc_tmem_ld32(lane_base + (uint32_t)((s * 2 + i) * TC2_BN + ch * 32), v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    tc_mbar_arrive(&t_empty[s * 2 + i]);                 // accumulator slot is free again (data in registers)
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store finished reading the tile
+                }
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-                        make_float4(v[qq][4 * j], v[qq][4 * j + 1], v[qq][4 * j + 2], v[qq][4 * j + 3]);
+                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                const int n0 = c * TC_BN + q * 32;
+                const int n0 = hc * TC2_BN + ch * 32;
                 if (lane == 0 && n0 < W) {
                     // 32 x 32 fp32 box, 128-byte swizzle (== the XOR pattern above); rows/columns beyond the tensor are clipped
                     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&out_map),
-                                 "r"(n0), "r"(e0 + wq * 32), "r"(tc_smem(stg))
+                                 "r"(n0), "r"(e0 + i * 128 + wq * 32), "r"(tc_smem(stg))
                                  : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
+                if (hc < 2 && i == 0) TC_STAMP(6 + 2 * hc);
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) tc_mbar_arrive(&t_empty[s]);
-            if (c < 3) TC_STAMP(6 + 2 * c);
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         TC_STAMP(11);
@@ -341,7 +361,7 @@ static int edge_mlp_tc_launch(const EdgeMlpTcArgs& t, cudaStream_t st) {
     }
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(edge_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        cudaFuncSetAttribute(edge_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES);
         attr_set = true;
     }
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -375,7 +395,7 @@ static int edge_mlp_tc_launch(const EdgeMlpTcArgs& t, cudaStream_t st) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     }
-    edge_hidden_kernel<<<dim3(min((int)grid.x, n_sm * 4)), EH_THREADS, 0, st>>>(a, t.himg);
-    edge_mlp_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(t, map);
+    edge_hidden_kernel<<<dim3(min((int)grid.x, n_sm * 4)), EH_THREADS, 0, st>>>(a, t.himg);   // 47 KB smem -> 4 CTAs per SM
+    edge_mlp_tc_kernel<<<dim3((a.n_edges + 255) / 256), TC_THREADS, TC2_SMEM_BYTES, st>>>(t, map);
     return dp_check_launch("edge_mlp_tc");
 }

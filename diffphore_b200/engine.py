@@ -80,17 +80,18 @@ class ConvWeights:
 
 def _make_w2img(w3, b3):
     """Shared-memory image of the second-layer weights for dp_edge_mlp_tc: W2aug[n, 0:60] = fc.3.weight, [n, 60] = bias,
-    zero padded to K = 64 and to a multiple of 128 columns, split into tf32 hi (round-to-nearest-away, like
-    cvt.rna.tf32.f32) and the fp32 remainder lo, stored per 128-column chunk as [hi|lo][k/4][n/8][n%8][k%4]."""
+    zero padded to K = 64 and to a multiple of 64 columns, split into tf32 hi (round-to-nearest-away, like
+    cvt.rna.tf32.f32) and the fp32 remainder lo, stored per 64-column half-chunk as [hi|lo][k/4][n/8][n%8][k%4]
+    (the canonical K-major no-swizzle core-matrix layout of the tcgen05 shared-memory descriptors)."""
     W = w3.shape[0]
-    nch = (W + 127) // 128
-    x = torch.zeros(nch * 128, 64, dtype=torch.float32)
+    nch = (W + 63) // 64
+    x = torch.zeros(nch * 64, 64, dtype=torch.float32)
     x[:W, :60] = w3
     x[:W, 60] = b3
     bits = x.view(torch.int32)
     hi = ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
     lo = x - hi
-    img = torch.stack([hi, lo], 0).reshape(2, nch, 16, 8, 16, 4).permute(1, 0, 4, 2, 3, 5)     # [c][h][kc][ng][r][j]
+    img = torch.stack([hi, lo], 0).reshape(2, nch, 8, 8, 16, 4).permute(1, 0, 4, 2, 3, 5)      # [c][h][kc][ng][r][j]
     return img.contiguous().reshape(-1)
 
 
