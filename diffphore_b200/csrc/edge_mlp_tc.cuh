@@ -99,9 +99,8 @@ __device__ long long* g_tc_dbg = nullptr;     // profiling aid: per-phase clock6
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// pass 1: hidden activations h = ReLU(W1 . attr + b1) for every edge, written as the shared-memory image of the
-// tensor-core A operand (per 128-edge tile: [k/4][row/8][row%8][k%4], k = 60 carries the constant 1 that multiplies the
-// bias row of W2aug, k = 61..63 zero).  256 B per edge (3-10 % of the per-edge weight stream); keeps the gather and
+// pass 1: hidden activations h = ReLU(W1 . attr + b1) for every edge, row-major [edge][64] (k = 60 carries the
+// constant 1 that multiplies the bias row of W2aug, k = 61..63 zero).  256 B per edge (3-10 % of the per-edge weight stream); keeps the gather and
 // the CUDA-core layer out of the tensor-core kernel, whose shared memory is full and cannot overlap them.
 // ---------------------------------------------------------------------------------------------------------------
 #define EH_THREADS 256
@@ -168,8 +167,7 @@ __global__ void __launch_bounds__(EH_THREADS) edge_hidden_kernel(EdgeMlpArgs a, 
 #pragma unroll
                 for (int j = 0; j < 8; ++j) h[i][j] = fmaf(am[i], bm[j], h[i][j]);
         }
-        // ReLU, constant-1 column (k = 60) and zero padding, then the tiled operand image [k/4][row/8][row%8][k%4]
-        float* out_tile = himg + (size_t)tile * (128 * TC_K) + (size_t)(2 * og) * 512 + m0 * 4;
+        // ReLU, constant-1 column (k = 60) and zero padding; row-major [edge][64] (256 B per edge)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             float r[8];
@@ -178,9 +176,9 @@ __global__ void __launch_bounds__(EH_THREADS) edge_hidden_kernel(EdgeMlpArgs a, 
                 const int o = o0 + j;
                 r[j] = o < 60 ? fmaxf(h[i][j], 0.f) : (o == 60 ? 1.0f : 0.f);
             }
-            // rows m0..m0+3 lie in one 8-row group (m0 is a multiple of 4): offset (m/8)*32 + (m%8)*4 == m*4
-            *reinterpret_cast<float4*>(out_tile + i * 4) = make_float4(r[0], r[1], r[2], r[3]);
-            *reinterpret_cast<float4*>(out_tile + 512 + i * 4) = make_float4(r[4], r[5], r[6], r[7]);
+            float* dst = himg + ((size_t)e0 + m0 + i) * TC_K + o0;
+            *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(r[4], r[5], r[6], r[7]);
         }
     }
 }
@@ -188,30 +186,54 @@ __global__ void __launch_bounds__(EH_THREADS) edge_hidden_kernel(EdgeMlpArgs a, 
 struct EdgeMlpTcArgs {
     EdgeMlpArgs base;        // w2t unused here
     const float* w2img;      // [ceil(W/64)][2 (hi, lo)][16 k-chunks][8 row groups][8 rows][4] fp32, zero padded
-    float* himg;             // scratch: [ceil(E/128)][16][16][8][4] hidden activations (edge_hidden_kernel)
+    float* himg;             // scratch: [E rounded up to 128][64] hidden activations (edge_hidden_kernel)
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// pass 2: w[256 edges, W] = h . W2aug on tcgen05.  One CTA owns TWO 128-edge tiles (A operands resident in shared
-// memory, hi/lo split = 128 KB) and streams the second-layer weights in 64-column half-chunks (32 KB, 2-stage TMA
-// ring): every weight byte fetched from L2 feeds 256 rows, which halves the L2->SM operand traffic that bounded the
-// one-tile version (it re-read 64 KB of weights for every 64 KB of output).  Per half-chunk: 2 x 24 MMAs
-// (M=128, N=64, K=8, kind::tf32; hi*hi + hi*lo + lo*hi) into 4 TMEM accumulator slots (2 stages x 2 tiles x 64 cols);
-// 8 epilogue warps drain one 32x32 block each per (half-chunk, tile): tcgen05.ld -> swizzled smem tile -> TMA store.
+// pass 2: w[256 edges, W] = h . W2aug on tcgen05.  One CTA owns TWO 128-edge tiles.  The A operands (hidden
+// activations, tf32 hi + fp32 remainder lo) live in TENSOR MEMORY (tcgen05.st, lane = edge row, 4 x 64 columns), so an
+// MMA only streams its B operand from shared memory: with both operands in smem the K=8 tf32 MMAs were bound by the
+// 128 B/clk shared-memory port (measured 81 clk per M128xN64xK8 instead of 34).  The second-layer weights stream in
+// 64-column half-chunks (hi|lo = 32 KB) through a 4-stage TMA ring; every weight byte fetched from L2 feeds 256 rows.
+// Per half-chunk: 2 x 24 MMAs (kind::tf32; hi*hi + hi*lo + lo*hi) into 4 accumulator slots (2 stages x 2 tiles x 64
+// columns); 8 epilogue warps drain one 32x32 block each per (half-chunk, tile): tcgen05.ld -> 128B-swizzled smem tile
+// -> TMA tensor store.  TMEM: 256 accumulator + 256 operand columns = all 512.
 // ---------------------------------------------------------------------------------------------------------------
 #define TC2_BN 64
+#define TC2_STAGES 4
 #define TC2_B_STAGE_BYTES (2 * TC2_BN * TC_K * 4)                 // hi + lo of a 64 x 64 fp32 block = 32 KB
-#define TC2_SMEM_BYTES (4 * TC_OPER_BYTES + 2 * TC2_B_STAGE_BYTES + 8 * 32 * 32 * 4 + 256)
+#define TC2_SMEM_BYTES (TC2_STAGES * TC2_B_STAGE_BYTES + 8 * 32 * 32 * 4 + 256)
+
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void tc_tmem_st32(uint32_t taddr, const float* v) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArgs args, const __grid_constant__ CUtensorMap out_map) {
     extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
     const EdgeMlpArgs& a = args.base;
-    float* a_op = reinterpret_cast<float*>(tc_smem_raw);              // [tile][hi|lo][128 x 64]
-    float* b_st = a_op + 4 * 128 * TC_K;                              // 2 stages x (hi 16 KB | lo 16 KB)
-    float* stg_all = b_st + 2 * 2 * TC2_BN * TC_K;                    // 8 x [32][32] swizzled transpose tiles
+    float* b_st = reinterpret_cast<float*>(tc_smem_raw);              // TC2_STAGES x (hi 16 KB | lo 16 KB)
+    float* stg_all = b_st + TC2_STAGES * 2 * TC2_BN * TC_K;           // 8 x [32][32] swizzled transpose tiles
     uint64_t* bars = reinterpret_cast<uint64_t*>(stg_all + 8 * 32 * 32);
-    uint64_t *b_full = bars, *b_empty = bars + 2, *t_full = bars + 4 /*[stage][tile]*/, *t_empty = bars + 8, *a_full = bars + 12;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    uint64_t *b_full = bars, *b_empty = bars + TC2_STAGES, *t_full = bars + 2 * TC2_STAGES /*[acc stage][tile]*/,
+             *t_empty = t_full + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int E = a.n_edges_dev ? *a.n_edges_dev : a.n_edges;
@@ -222,13 +244,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
 
     TC_STAMP(0);
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) { tc_mbar_init(&b_full[i], 1); tc_mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < TC2_STAGES; ++i) { tc_mbar_init(&b_full[i], 1); tc_mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 4; ++i) { tc_mbar_init(&t_full[i], 1); tc_mbar_init(&t_empty[i], TC_WORKERS / 32); }
-        tc_mbar_init(a_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(tc_smem(tmem_slot)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tc_smem(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -237,68 +258,74 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
     const uint32_t tmem_base = *tmem_slot;
     TC_STAMP(1);
 
-    if (tid == TC_WORKERS) {
-        // A images (fp32 hidden activations written by edge_hidden_kernel) land in the hi slots; first weight half-chunk
-        tc_mbar_expect_tx(a_full, ntile * TC_OPER_BYTES);
-        for (int i = 0; i < ntile; ++i)
-            tc_bulk_load(a_op + i * 2 * 128 * TC_K, args.himg + ((size_t)blockIdx.x * 2 + i) * (128 * TC_K), TC_OPER_BYTES, a_full);
-        tc_mbar_expect_tx(&b_full[0], TC2_B_STAGE_BYTES);
-        tc_bulk_load(b_st, args.w2img, TC2_B_STAGE_BYTES, &b_full[0]);
+    if (tid == TC_WORKERS) {                                          // start streaming the weights right away
+        for (int st = 0; st < TC2_STAGES - 1 && st < nhc; ++st) {
+            tc_mbar_expect_tx(&b_full[st], TC2_B_STAGE_BYTES);
+            tc_bulk_load(b_st + st * 2 * TC2_BN * TC_K, args.w2img + (size_t)st * 2 * TC2_BN * TC_K, TC2_B_STAGE_BYTES, &b_full[st]);
+        }
     }
     if (warp < 8) {
-        // split the fp32 activations into tf32 hi + remainder lo, in place (3xTF32)
-        tc_mbar_wait(a_full, 0);
-        TC_STAMP(2);
-        for (int i = 0; i < ntile; ++i) {
-            float* hi_p = a_op + i * 2 * 128 * TC_K;
-            float* lo_p = hi_p + 128 * TC_K;
+        // A operands -> tensor memory: thread (tile = tid / 128, row = tid % 128) loads its edge's 64 hidden activations,
+        // splits them into tf32 hi + remainder lo (3xTF32) and stores both as 64 TMEM columns of its lane.
+        const int tile = tid >> 7, row = tid & 127, wq = warp & 3;
+        if (tile < ntile) {
+            const int e = min(e0 + tile * 128 + row, E - 1);
+            const float4* hp = reinterpret_cast<const float4*>(args.himg + (size_t)e * TC_K);
+            const uint32_t a_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + 256u + (uint32_t)(tile * 128);
 #pragma unroll
-            for (int t = 0; t < (128 * TC_K / 4) / TC_WORKERS; ++t) {
-                const int o = (tid + TC_WORKERS * t) * 4;
-                const float4 h = *reinterpret_cast<const float4*>(hi_p + o);
-                const float4 hi = make_float4(tc_tf32_rna(h.x), tc_tf32_rna(h.y), tc_tf32_rna(h.z), tc_tf32_rna(h.w));
-                *reinterpret_cast<float4*>(hi_p + o) = hi;
-                *reinterpret_cast<float4*>(lo_p + o) = make_float4(h.x - hi.x, h.y - hi.y, h.z - hi.z, h.w - hi.w);
+            for (int half = 0; half < 2; ++half) {
+                float hi[32], lo[32];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 h = __ldg(hp + half * 8 + q);
+                    hi[4 * q] = tc_tf32_rna(h.x); hi[4 * q + 1] = tc_tf32_rna(h.y);
+                    hi[4 * q + 2] = tc_tf32_rna(h.z); hi[4 * q + 3] = tc_tf32_rna(h.w);
+                    lo[4 * q] = h.x - hi[4 * q]; lo[4 * q + 1] = h.y - hi[4 * q + 1];
+                    lo[4 * q + 2] = h.z - hi[4 * q + 2]; lo[4 * q + 3] = h.w - hi[4 * q + 3];
+                }
+                tc_tmem_st32(a_addr + (uint32_t)(half * 32), hi);            // hi: columns [0, 64) of the tile's operand block
+                tc_tmem_st32(a_addr + 64u + (uint32_t)(half * 32), lo);      // lo: columns [64, 128)
             }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy (MMA) reads
         TC_STAMP(3);
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     TC_STAMP(4);
 
     if (tid == TC_WORKERS) {
         // ================= TMA producer + MMA issuer (single thread) =================
-        // instruction descriptor: D=F32, A=B=TF32, K-major both, N=64, M=128
+        // instruction descriptor: D=F32, A=B=TF32, K-major, N=64, M=128
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC2_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         for (int hc = 0; hc < nhc; ++hc) {
-            const int s = hc & 1, u = hc >> 1;
-            if (hc + 1 < nhc) {
-                const int s1 = (hc + 1) & 1, u1 = (hc + 1) >> 1;
+            const int s = hc % TC2_STAGES, u = hc / TC2_STAGES, as = hc & 1, au = hc >> 1;
+            const int nx = hc + TC2_STAGES - 1;                       // keep TC2_STAGES-1 weight loads in flight
+            if (nx < nhc) {
+                const int s1 = nx % TC2_STAGES, u1 = nx / TC2_STAGES;
                 tc_mbar_wait(&b_empty[s1], (u1 & 1) ^ 1);
                 tc_mbar_expect_tx(&b_full[s1], TC2_B_STAGE_BYTES);
-                tc_bulk_load(b_st + s1 * 2 * TC2_BN * TC_K, args.w2img + (size_t)(hc + 1) * 2 * TC2_BN * TC_K, TC2_B_STAGE_BYTES,
-                             &b_full[s1]);
+                tc_bulk_load(b_st + s1 * 2 * TC2_BN * TC_K, args.w2img + (size_t)nx * 2 * TC2_BN * TC_K, TC2_B_STAGE_BYTES, &b_full[s1]);
             }
             tc_mbar_wait(&b_full[s], u & 1);
             const uint32_t b_hi_s = tc_smem(b_st + s * 2 * TC2_BN * TC_K), b_lo_s = b_hi_s + TC2_BN * TC_K * 4;
             for (int i = 0; i < ntile; ++i) {
-                tc_mbar_wait(&t_empty[s * 2 + i], (u & 1) ^ 1);
+                tc_mbar_wait(&t_empty[as * 2 + i], (au & 1) ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_hi_s = tc_smem(a_op + i * 2 * 128 * TC_K), a_lo_s = a_hi_s + TC_OPER_BYTES;
-                const uint32_t d = tmem_base + (uint32_t)((s * 2 + i) * TC2_BN);
+                const uint32_t a_hi_t = tmem_base + 256u + (uint32_t)(i * 128), a_lo_t = a_hi_t + 64u;
+                const uint32_t d = tmem_base + (uint32_t)((as * 2 + i) * TC2_BN);
 #pragma unroll
                 for (int combo = 0; combo < 3; ++combo) {
-                    const uint32_t as = combo == 2 ? a_lo_s : a_hi_s;
+                    const uint32_t at = combo == 2 ? a_lo_t : a_hi_t;
                     const uint32_t bs = combo == 1 ? b_lo_s : b_hi_s;
 #pragma unroll
                     for (int ks = 0; ks < TC_K / 8; ++ks) {
-                        const uint64_t ad = tc_smem_desc(as + ks * 2 * 2048, 2048, 128);      // 16 row groups per K chunk
                         const uint64_t bd = tc_smem_desc(bs + ks * 2 * 1024, 1024, 128);      // 8 row groups per K chunk
-                        tc_mma_tf32(d, ad, bd, idesc, (combo | ks) ? 1u : 0u);
+                        tc_mma_tf32_ts(d, at + (uint32_t)(ks * 8), bd, idesc, (combo | ks) ? 1u : 0u);
                     }
                 }
-                tc_commit(&t_full[s * 2 + i]);    // accumulator slot complete
+                tc_commit(&t_full[as * 2 + i]);   // accumulator slot complete
             }
             tc_commit(&b_empty[s]);               // weight stage reusable once all MMAs above have read it
         }
@@ -309,18 +336,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
         const int wq = warp & 3, ch = warp >> 2;
         const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
         for (int hc = 0; hc < nhc; ++hc) {
-            const int s = hc & 1, u = hc >> 1;
+            const int as = hc & 1, au = hc >> 1;
             for (int i = 0; i < ntile; ++i) {
-                tc_mbar_wait(&t_full[s * 2 + i], u & 1);
+                tc_mbar_wait(&t_full[as * 2 + i], au & 1);
                 if (hc < 2 && i == 0) TC_STAMP(5 + 2 * hc);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 float v[32];
-                tc_tmem_ld32(lane_base + (uint32_t)((s * 2 + i) * TC2_BN + ch * 32), v);
+                tc_tmem_ld32(lane_base + (uint32_t)((as * 2 + i) * TC2_BN + ch * 32), v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) {
-                    tc_mbar_arrive(&t_empty[s * 2 + i]);                 // accumulator slot is free again (data in registers)
+                    tc_mbar_arrive(&t_empty[as * 2 + i]);                // accumulator slot is free again (data in registers)
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store finished reading the tile
                 }
                 __syncwarp();
@@ -348,7 +375,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
     __syncthreads();
     TC_STAMP(12);
     if (warp == 8) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
 }
 
