@@ -122,7 +122,7 @@ int dp_edge_mlp(const float* emb, const int32_t* perm, const float* tb, const in
 
 int dp_edge_mlp_tc(const float* emb, const int32_t* perm, const float* tb, const int32_t* idxB, int32_t strideB,
                    const float* tc, const int32_t* idxC, const int32_t* idxC2, int32_t strideC, const float* w1,
-                   const float* b1, const float* w2img, int32_t in_dim, int32_t hid, int32_t W,
+                   const float* b1, const void* w2img, float inv_wscale, int32_t in_dim, int32_t hid, int32_t W,
                    const int32_t* n_edges_dev, int32_t n_edges_cap, float* h_scratch, float* w_out, void* stream) {
     EdgeMlpTcArgs t;
     EdgeMlpArgs& a = t.base;
@@ -130,6 +130,7 @@ int dp_edge_mlp_tc(const float* emb, const int32_t* perm, const float* tb, const
     a.strideC = strideC; a.w1 = w1; a.b1 = b1; a.w2t = nullptr; a.in_dim = in_dim; a.hid = hid; a.W = W;
     a.n_edges_dev = n_edges_dev; a.n_edges = n_edges_cap; a.out = w_out;
     t.w2img = w2img;
+    t.inv_wscale = inv_wscale;
     t.himg = h_scratch;
     return edge_mlp_tc_launch(t, ST(stream));
 }

@@ -11,6 +11,7 @@
 // ~4k clk of this SM's share of HBM write bandwidth: the kernel is HBM-write-bound by design.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "edge_mlp.cuh"
 
@@ -185,35 +186,39 @@ __global__ void __launch_bounds__(EH_THREADS) edge_hidden_kernel(EdgeMlpArgs a, 
 
 struct EdgeMlpTcArgs {
     EdgeMlpArgs base;        // w2t unused here
-    const float* w2img;      // [ceil(W/64)][2 (hi, lo)][16 k-chunks][8 row groups][8 rows][4] fp32, zero padded
+    const void* w2img;       // [ceil(W/64)][2 (hi, lo)][8 k-chunks][8 row groups][8 rows][8] fp16 of W2aug * wscale, zero padded
+    float inv_wscale;        // 1 / wscale (power of two)
     float* himg;             // scratch: [E rounded up to 128][64] hidden activations (edge_hidden_kernel)
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// pass 2: w[256 edges, W] = h . W2aug on tcgen05.  One CTA owns TWO 128-edge tiles.  The A operands (hidden
-// activations, tf32 hi + fp32 remainder lo) live in TENSOR MEMORY (tcgen05.st, lane = edge row, 4 x 64 columns), so an
-// MMA only streams its B operand from shared memory: with both operands in smem the K=8 tf32 MMAs were bound by the
-// 128 B/clk shared-memory port (measured 81 clk per M128xN64xK8 instead of 34).  The second-layer weights stream in
-// 64-column half-chunks (hi|lo = 32 KB) through a 4-stage TMA ring; every weight byte fetched from L2 feeds 256 rows.
-// Per half-chunk: 2 x 24 MMAs (kind::tf32; hi*hi + hi*lo + lo*hi) into 4 accumulator slots (2 stages x 2 tiles x 64
-// columns); 8 epilogue warps drain one 32x32 block each per (half-chunk, tile): tcgen05.ld -> 128B-swizzled smem tile
-// -> TMA tensor store.  TMEM: 256 accumulator + 256 operand columns = all 512.
+// pass 2: w[256 edges, W] = h . W2aug on tcgen05.  One CTA owns TWO 128-edge tiles.
+//  * fp32 parity through a 2-way FP16 split with exact power-of-two scaling: every row of h is scaled so that its
+//    largest entry lies in [2^12, 2^13) and W2aug by one per-layer power of two, then x = hi + lo with hi = fp16(x),
+//    lo = fp16(x - hi) (22 significant bits, the same as a tf32 hi/lo split) and the three products hi*hi + hi*lo +
+//    lo*hi are accumulated in fp32 by kind::f16 MMAs; the scales are undone exactly in the epilogue.  Compared with
+//    3xTF32 this halves the MMA time (K = 16 per instruction at the same instruction cost) and the operand bytes.
+//  * A operands live in TENSOR MEMORY (tcgen05.st, lane = edge row, 2 tiles x (32 hi + 32 lo) columns of packed
+//    half2), B (64-column half-chunks, hi|lo = 16 KB) streams through a 6-stage TMA ring: each weight byte fetched
+//    from L2 feeds 256 rows.
+//  * Per half-chunk: 2 x 12 MMAs (M=128, N=64, K=16) into 4 accumulator slots (2 stages x 2 tiles x 64 columns); 8
+//    epilogue warps drain one 32x32 block each per (half-chunk, tile): tcgen05.ld -> rescale -> 128B-swizzled smem
+//    tile -> TMA tensor store.
 // ---------------------------------------------------------------------------------------------------------------
 #define TC2_BN 64
-#define TC2_STAGES 4
-#define TC2_B_STAGE_BYTES (2 * TC2_BN * TC_K * 4)                 // hi + lo of a 64 x 64 fp32 block = 32 KB
-#define TC2_SMEM_BYTES (TC2_STAGES * TC2_B_STAGE_BYTES + 8 * 32 * 32 * 4 + 256)
+#define TC2_STAGES 6
+#define TC2_B_STAGE_BYTES (2 * TC2_BN * TC_K * 2)                 // hi + lo of a 64 x 64 fp16 block = 16 KB
+#define TC2_SMEM_BYTES (TC2_STAGES * TC2_B_STAGE_BYTES + 8 * 32 * 32 * 4 + 256 * 4 + 256)
 
-__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
-__device__ __forceinline__ void tc_tmem_st32(uint32_t taddr, const float* v) {
-    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+__device__ __forceinline__ void tc_tmem_st32(uint32_t taddr, const uint32_t* r) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
         "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
@@ -224,13 +229,17 @@ __device__ __forceinline__ void tc_tmem_st32(uint32_t taddr, const float* v) {
           "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
+__device__ __forceinline__ uint32_t tc_pack_half2(__half lo16, __half hi16) {
+    return (uint32_t)__half_as_ushort(lo16) | ((uint32_t)__half_as_ushort(hi16) << 16);
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArgs args, const __grid_constant__ CUtensorMap out_map) {
     extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
     const EdgeMlpArgs& a = args.base;
-    float* b_st = reinterpret_cast<float*>(tc_smem_raw);              // TC2_STAGES x (hi 16 KB | lo 16 KB)
-    float* stg_all = b_st + TC2_STAGES * 2 * TC2_BN * TC_K;           // 8 x [32][32] swizzled transpose tiles
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stg_all + 8 * 32 * 32);
+    uint8_t* b_st = tc_smem_raw;                                      // TC2_STAGES x (hi 8 KB | lo 8 KB), fp16
+    float* stg_all = reinterpret_cast<float*>(b_st + TC2_STAGES * TC2_B_STAGE_BYTES);     // 8 x [32][32] swizzled tiles
+    float* row_scale = stg_all + 8 * 32 * 32;                         // [256] 1 / (row scale * weight scale)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(row_scale + 256);
     uint64_t *b_full = bars, *b_empty = bars + TC2_STAGES, *t_full = bars + 2 * TC2_STAGES /*[acc stage][tile]*/,
              *t_empty = t_full + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 4);
@@ -261,31 +270,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
     if (tid == TC_WORKERS) {                                          // start streaming the weights right away
         for (int st = 0; st < TC2_STAGES - 1 && st < nhc; ++st) {
             tc_mbar_expect_tx(&b_full[st], TC2_B_STAGE_BYTES);
-            tc_bulk_load(b_st + st * 2 * TC2_BN * TC_K, args.w2img + (size_t)st * 2 * TC2_BN * TC_K, TC2_B_STAGE_BYTES, &b_full[st]);
+            tc_bulk_load(b_st + st * TC2_B_STAGE_BYTES, reinterpret_cast<const uint8_t*>(args.w2img) + (size_t)st * TC2_B_STAGE_BYTES,
+                         TC2_B_STAGE_BYTES, &b_full[st]);
         }
     }
     if (warp < 8) {
         // A operands -> tensor memory: thread (tile = tid / 128, row = tid % 128) loads its edge's 64 hidden activations,
-        // splits them into tf32 hi + remainder lo (3xTF32) and stores both as 64 TMEM columns of its lane.
+        // scales the row by a power of two, splits into fp16 hi + lo and stores both as 32 packed TMEM columns of its lane.
         const int tile = tid >> 7, row = tid & 127, wq = warp & 3;
         if (tile < ntile) {
             const int e = min(e0 + tile * 128 + row, E - 1);
             const float4* hp = reinterpret_cast<const float4*>(args.himg + (size_t)e * TC_K);
-            const uint32_t a_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + 256u + (uint32_t)(tile * 128);
+            float h[64];
+            float m = 0.f;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float hi[32], lo[32];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 h = __ldg(hp + half * 8 + q);
-                    hi[4 * q] = tc_tf32_rna(h.x); hi[4 * q + 1] = tc_tf32_rna(h.y);
-                    hi[4 * q + 2] = tc_tf32_rna(h.z); hi[4 * q + 3] = tc_tf32_rna(h.w);
-                    lo[4 * q] = h.x - hi[4 * q]; lo[4 * q + 1] = h.y - hi[4 * q + 1];
-                    lo[4 * q + 2] = h.z - hi[4 * q + 2]; lo[4 * q + 3] = h.w - hi[4 * q + 3];
-                }
-                tc_tmem_st32(a_addr + (uint32_t)(half * 32), hi);            // hi: columns [0, 64) of the tile's operand block
-                tc_tmem_st32(a_addr + 64u + (uint32_t)(half * 32), lo);      // lo: columns [64, 128)
+            for (int q = 0; q < 16; ++q) {
+                const float4 v = __ldg(hp + q);
+                h[4 * q] = v.x; h[4 * q + 1] = v.y; h[4 * q + 2] = v.z; h[4 * q + 3] = v.w;
+                m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
             }
+            // s = 2^(12 - floor(log2 m)): m * s in [2^12, 2^13); m >= 1 always (the bias column holds 1.0)
+            const int ex = (int)((__float_as_uint(m) >> 23) & 0xFF) - 127;
+            const float sc = __uint_as_float((uint32_t)(127 + 12 - ex) << 23);
+            const float isc = __uint_as_float((uint32_t)(127 - 12 + ex) << 23);
+            row_scale[tid] = isc * args.inv_wscale;
+            uint32_t hi_p[32], lo_p[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const float x0 = h[2 * c] * sc, x1 = h[2 * c + 1] * sc;
+                const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+                hi_p[c] = tc_pack_half2(h0, h1);
+                lo_p[c] = tc_pack_half2(__float2half_rn(x0 - __half2float(h0)), __float2half_rn(x1 - __half2float(h1)));
+            }
+            const uint32_t a_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + 256u + (uint32_t)(tile * 64);
+            tc_tmem_st32(a_addr, hi_p);                               // hi: columns [0, 32) of the tile's operand block
+            tc_tmem_st32(a_addr + 32u, lo_p);                         // lo: columns [32, 64)
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
         TC_STAMP(3);
@@ -297,8 +316,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
 
     if (tid == TC_WORKERS) {
         // ================= TMA producer + MMA issuer (single thread) =================
-        // instruction descriptor: D=F32, A=B=TF32, K-major, N=64, M=128
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC2_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        // instruction descriptor: D=F32 (c_format 1), A=B=F16 (format 0), K-major, N=64, M=128
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(TC2_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         for (int hc = 0; hc < nhc; ++hc) {
             const int s = hc % TC2_STAGES, u = hc / TC2_STAGES, as = hc & 1, au = hc >> 1;
             const int nx = hc + TC2_STAGES - 1;                       // keep TC2_STAGES-1 weight loads in flight
@@ -306,23 +325,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
                 const int s1 = nx % TC2_STAGES, u1 = nx / TC2_STAGES;
                 tc_mbar_wait(&b_empty[s1], (u1 & 1) ^ 1);
                 tc_mbar_expect_tx(&b_full[s1], TC2_B_STAGE_BYTES);
-                tc_bulk_load(b_st + s1 * 2 * TC2_BN * TC_K, args.w2img + (size_t)nx * 2 * TC2_BN * TC_K, TC2_B_STAGE_BYTES, &b_full[s1]);
+                tc_bulk_load(b_st + s1 * TC2_B_STAGE_BYTES, reinterpret_cast<const uint8_t*>(args.w2img) + (size_t)nx * TC2_B_STAGE_BYTES,
+                             TC2_B_STAGE_BYTES, &b_full[s1]);
             }
             tc_mbar_wait(&b_full[s], u & 1);
-            const uint32_t b_hi_s = tc_smem(b_st + s * 2 * TC2_BN * TC_K), b_lo_s = b_hi_s + TC2_BN * TC_K * 4;
+            const uint32_t b_hi_s = tc_smem(b_st + s * TC2_B_STAGE_BYTES), b_lo_s = b_hi_s + TC2_B_STAGE_BYTES / 2;
             for (int i = 0; i < ntile; ++i) {
                 tc_mbar_wait(&t_empty[as * 2 + i], (au & 1) ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_hi_t = tmem_base + 256u + (uint32_t)(i * 128), a_lo_t = a_hi_t + 64u;
+                const uint32_t a_hi_t = tmem_base + 256u + (uint32_t)(i * 64), a_lo_t = a_hi_t + 32u;
                 const uint32_t d = tmem_base + (uint32_t)((as * 2 + i) * TC2_BN);
 #pragma unroll
                 for (int combo = 0; combo < 3; ++combo) {
                     const uint32_t at = combo == 2 ? a_lo_t : a_hi_t;
                     const uint32_t bs = combo == 1 ? b_lo_s : b_hi_s;
 #pragma unroll
-                    for (int ks = 0; ks < TC_K / 8; ++ks) {
-                        const uint64_t bd = tc_smem_desc(bs + ks * 2 * 1024, 1024, 128);      // 8 row groups per K chunk
-                        tc_mma_tf32_ts(d, at + (uint32_t)(ks * 8), bd, idesc, (combo | ks) ? 1u : 0u);
+                    for (int ks = 0; ks < TC_K / 16; ++ks) {
+                        // fp16 K-major no-swizzle: core matrix = 8 rows x 8 halfs; K chunk stride 8 x 128 B, 2 chunks per MMA
+                        const uint64_t bd = tc_smem_desc(bs + ks * 2 * 1024, 1024, 128);
+                        tc_mma_f16_ts(d, at + (uint32_t)(ks * 8), bd, idesc, (combo | ks) ? 1u : 0u);
                     }
                 }
                 tc_commit(&t_full[as * 2 + i]);   // accumulator slot complete
@@ -335,6 +356,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
         float* stg = stg_all + warp * 32 * 32;
         const int wq = warp & 3, ch = warp >> 2;
         const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
+        const float rs[2] = {row_scale[wq * 32 + lane], row_scale[128 + wq * 32 + lane]};
         for (int hc = 0; hc < nhc; ++hc) {
             const int as = hc & 1, au = hc >> 1;
             for (int i = 0; i < ntile; ++i) {
@@ -351,10 +373,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_mlp_tc_kernel(EdgeMlpTcArg
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store finished reading the tile
                 }
                 __syncwarp();
+                const float r = rs[i];
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        make_float4(v[4 * j] * r, v[4 * j + 1] * r, v[4 * j + 2] * r, v[4 * j + 3] * r);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 const int n0 = hc * TC2_BN + ch * 32;

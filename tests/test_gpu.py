@@ -231,14 +231,15 @@ def test_edge_mlp_tensor_core_path_matches_ffma_path(built_lib, W, E):
     w1, b1 = (torch.randn(60, 60, generator=g) * 0.2).to(dev), torch.randn(60, generator=g).to(dev)
     w3, b3 = torch.randn(W, 60, generator=g) * 0.5, torch.randn(W, generator=g)
     w2t = torch.cat([w3.T, b3[None]], 0).contiguous().to(dev)
-    img = _make_w2img(w3, b3).to(dev)
+    img, inv_ws = _make_w2img(w3, b3)
+    img = img.to(dev)
     n_dev = torch.tensor([E], dtype=torch.int32, device=dev)
     out_f, out_t = torch.zeros(E + 200, W, device=dev), torch.full((E + 200, W), 7.0, device=dev)
     hbuf = torch.empty(((E + 200 + 127) // 128) * 128 * 64, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     built_lib.check(lib.dp_edge_mlp(p(emb), None, p(nb), p(ib), 50, p(nc), p(ic), None, 80, p(w1), p(b1), p(w2t), 60, 60, W,
                                     p(n_dev), E + 200, p(out_f), st))
-    built_lib.check(lib.dp_edge_mlp_tc(p(emb), None, p(nb), p(ib), 50, p(nc), p(ic), None, 80, p(w1), p(b1), p(img), 60, 60, W,
+    built_lib.check(lib.dp_edge_mlp_tc(p(emb), None, p(nb), p(ib), 50, p(nc), p(ic), None, 80, p(w1), p(b1), p(img), inv_ws, 60, 60, W,
                                        p(n_dev), E + 200, p(hbuf), p(out_t), st))
     torch.cuda.synchronize()
     attr = torch.cat([emb, nb[ib.long(), :20], nc[ic.long(), :20]], 1).double()

@@ -13,18 +13,18 @@ for W in (600, 2200):
     emb = torch.randn(E, 20, generator=g).to(dev); nodes = torch.randn(5000, 100, generator=g).to(dev)
     ib = torch.randint(0, 5000, (E,), generator=g, dtype=torch.int32).to(dev); ic = torch.randint(0, 5000, (E,), generator=g, dtype=torch.int32).to(dev)
     w1, b1 = torch.randn(60, 60).to(dev), torch.randn(60).to(dev)
-    img = _make_w2img(torch.randn(W, 60), torch.randn(W)).to(dev)
+    img, inv_ws = _make_w2img(torch.randn(W, 60), torch.randn(W)); img = img.to(dev)
     out = torch.empty(E, W, device=dev)
     hbuf = torch.empty(E * 64, device=dev)
     dbg = torch.zeros(64, dtype=torch.int64, device=dev)
     raw.dp_debug_set_tc_probe(ctypes.c_void_p(dbg.data_ptr()))
     st = torch.cuda.current_stream().cuda_stream
     for _ in range(3):
-        L.check(lib.dp_edge_mlp_tc(p(emb), None, p(nodes), p(ib), 100, p(nodes), p(ic), None, 100, p(w1), p(b1), p(img), 60, 60, W, None, E, p(hbuf), p(out), st))
+        L.check(lib.dp_edge_mlp_tc(p(emb), None, p(nodes), p(ib), 100, p(nodes), p(ic), None, 100, p(w1), p(b1), p(img), inv_ws, 60, 60, W, None, E, p(hbuf), p(out), st))
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    L.check(lib.dp_edge_mlp_tc(p(emb), None, p(nodes), p(ib), 100, p(nodes), p(ic), None, 100, p(w1), p(b1), p(img), 60, 60, W, None, E, p(hbuf), p(out), st))
+    L.check(lib.dp_edge_mlp_tc(p(emb), None, p(nodes), p(ib), 100, p(nodes), p(ic), None, 100, p(w1), p(b1), p(img), inv_ws, 60, 60, W, None, E, p(hbuf), p(out), st))
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     d = dbg.cpu().tolist()
