@@ -104,30 +104,33 @@ __device__ long long* g_tc_dbg = nullptr;     // profiling aid: per-phase clock6
 // constant 1 that multiplies the bias row of W2aug, k = 61..63 zero).  256 B per edge (3-10 % of the per-edge weight stream); keeps the gather and
 // the CUDA-core layer out of the tensor-core kernel, whose shared memory is full and cannot overlap them.
 // ---------------------------------------------------------------------------------------------------------------
-#define EH_THREADS 256
-#define EH_LD 132                   // padded row length of the transposed attribute tile
-__global__ void __launch_bounds__(EH_THREADS) edge_hidden_kernel(EdgeMlpArgs a, float* __restrict__ himg) {
-    // register-tiled SGEMM  h[128 edges, 64] = attr[128, 60] . W1T[60, 64]: a thread owns 4 edges x 8 outputs, per k it
-    // reads 4 attributes (one float4 of the k-major tile) and 8 weights (two broadcast float4) for 32 FMAs.
+#define EH_THREADS 128
+#define EH_TILE 64                  // edges per CTA iteration
+#define EH_LD 68                    // padded row length of the transposed attribute tile
+__global__ void __launch_bounds__(EH_THREADS, 6) edge_hidden_kernel(EdgeMlpArgs a, float* __restrict__ himg) {
+    // register-tiled SGEMM  h[64 edges, 64] = attr[64, 60] . W1T[60, 64]: a thread owns 4 edges x 8 outputs, per k it
+    // reads 4 attributes (one float4 of the k-major tile) and 8 weights (two broadcast float4) for 32 FMAs.  Small tiles
+    // (32 KB of shared memory, <= 80 registers) keep 6-7 CTAs resident per SM so that the two dependent gather round
+    // trips (index -> row) of one CTA overlap the FMA phase of the others.
     __shared__ __align__(16) float w1t[60 * 64];          // [k][o], o >= 60 zero
     __shared__ __align__(16) float attrT[60 * EH_LD];     // [c][m]
     const int tid = threadIdx.x;
     const int E = a.n_edges_dev ? *a.n_edges_dev : a.n_edges;
-    const int ntiles = (E + 127) / 128;
+    const int ntiles = (E + EH_TILE - 1) / EH_TILE;
     if ((int)blockIdx.x >= ntiles) return;
     for (int i = tid; i < 60 * 64; i += EH_THREADS) {
         const int k = i >> 6, o = i & 63;
         w1t[i] = o < 60 ? a.w1[o * 60 + k] : 0.f;
     }
-    const int mg = tid & 31, og = tid >> 5, m0 = 4 * mg, o0 = 8 * og;
+    const int mg = tid & 15, og = tid >> 4, m0 = 4 * mg, o0 = 8 * og;
     float bias[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) bias[j] = (o0 + j < 60) ? a.b1[o0 + j] : 0.f;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {          // persistent: W1 is staged once per CTA
-        const int e0 = tile * 128;
+        const int e0 = tile * EH_TILE;
         __syncthreads();                                                     // previous tile fully consumed
         {
-            constexpr int NT = 128 * 30 / EH_THREADS;                        // 15 float2 items per thread, coalesced by part
+            constexpr int NT = EH_TILE * 30 / EH_THREADS;                    // 15 float2 items per thread, coalesced by part
             int ridx[NT], ridx2[NT];
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
@@ -445,7 +448,7 @@ static int edge_mlp_tc_launch(const EdgeMlpTcArgs& t, cudaStream_t st) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     }
-    edge_hidden_kernel<<<dim3(min((int)grid.x, n_sm * 4)), EH_THREADS, 0, st>>>(a, t.himg);   // 47 KB smem -> 4 CTAs per SM
+    edge_hidden_kernel<<<dim3(min((a.n_edges + EH_TILE - 1) / EH_TILE, n_sm * 6)), EH_THREADS, 0, st>>>(a, t.himg);
     edge_mlp_tc_kernel<<<dim3((a.n_edges + 255) / 256), TC_THREADS, TC2_SMEM_BYTES, st>>>(t, map);
     return dp_check_launch("edge_mlp_tc");
 }
