@@ -1,0 +1,594 @@
+// dp_conv_fused: one TensorProductConvLayer (score_model_phore.py:134-149) WITHOUT materialising the per-edge
+// tensor-product weights in HBM.
+//
+//   w[e, 0:W]   = [h(e) | 1] . W2aug                     tcgen05 tensor cores, accumulators in tensor memory (K5)
+//   tp[e]       = FCTP(node_in[gather[e]], sh[e], w[e])   CUDA cores, thread = edge, w read straight from TMEM (K6)
+//   out[n]      = BatchNorm(mean_{e in seg(n)} tp[e]) (+ residual)      shared-memory segmented reduction (K7, K8)
+//
+// The unfused pipeline (dp_edge_mlp_tc -> dp_tp_scatter) writes and re-reads 4*W bytes per edge (2.4-8.8 KB): both
+// of its kernels are HBM-bound on that stream.  Here the weights only ever exist as a [128 edges x 100 columns] fp32
+// tile in tensor memory, which turns the convolution into a tensor-pipe-bound kernel ("a K5->K6-fused
+// kernel never materialises weights: report against the FLOP roofline").
+//
+// Work decomposition
+//   * Edges are grouped by output node (CSR seg_ptr).  TILES are runs of whole nodes with <= 128 edges (tile_node[],
+//     built by dp_build_tiles or on the host), so the edge->node reduction never leaves the CTA: no atomics, the sum
+//     over a node's edges is sequential in edge order => bit-identical results for any batch composition.
+//   * A persistent CTA processes PAIRS of tiles (256 edges): every 100-column weight chunk fetched from L2 by TMA
+//     feeds two M=128 MMA groups.  Warps 0-3 own the 128 TMEM lanes of tile 0, warps 4-7 those of tile 1 (thread =
+//     edge for the whole pair), warp 8 is the TMA producer + MMA issuer.
+//   * fp32 parity: exactly-scaled 2-way FP16 split of both operands (hi*hi + hi*lo + lo*hi, fp32 accumulation), see
+//     edge_mlp_tc.cuh.  A operands live in tensor memory (tcgen05.st), B streams through a TMA ring.
+//   * The per-path weight blocks [U x V] are all multiples of 100 columns, so a chunk = 100 consecutive columns of the
+//     e3nn weight layout = 5 rows (V = 20) or 10 rows (V = 10) of one path; MMA N = 112 (100 + zero padding).
+//     TMEM: 3 accumulator slots x 128 columns rotate over the (chunk, tile) items, A operands in columns 384..511.
+#pragma once
+#include "edge_mlp_tc.cuh"
+#include "tp_tables.cuh"
+
+#define CF_WORKERS 256
+#define CF_THREADS 352                                // + warps 8, 9: MMA issuers of tile 0 / tile 1, warp 10: TMA producer
+#define CF_CHUNK 100                                  // weight columns per chunk
+#define CF_N 112                                      // MMA N (chunk padded to a multiple of 16)
+#define CF_B_HALF (CF_N * TC_K * 2)                   // one fp16 operand image (hi or lo) of a chunk: 14336 B
+#define CF_B_STAGE (2 * CF_B_HALF)                    // hi | lo
+#define CF_XB 32                                      // node rows per gather batch of a warp
+#define CF_SLOTS 4                                    // accumulator slots (TMEM), rotating over the (chunk, tile) items
+#define CF_SLOT_COLS 112
+#define CF_A_COL 448                                  // A hi operands: tile t -> TMEM columns 448 + 32 t
+#define CF_ALO_TILE (128 * TC_K * 2)                  // A lo operand of one tile in shared memory (K-major core matrices): 16 KB
+
+// profiling aid (tools/conv_fused_probe.py --stamps): clock64() stamps of CTA 0, second pair; role 0 = MMA issuer,
+// 1 = warp 0, 2 = warp 4; [role][item (< 64)][3]
+#define CF_STAMP(role, idx, k) do { if (PROBE && blockIdx.x == 0 && probe_on && (idx) < 64) a_dbg[((role) * 64 + (idx)) * 3 + (k)] = clock64(); } while (0)
+
+struct ConvFusedArgs {
+    const float* himg;          // [E][64] hidden activations (edge_hidden_kernel), edge order = seg order
+    const void* w2img;          // [W/100][hi|lo][8 k-chunks][14 row groups][8 rows][8] fp16 of W2aug * wscale
+    float inv_wscale;
+    const float* node_in;       // [n_in, D_IN]
+    const int* gather_idx;      // [E] row of node_in per edge (nullptr: identity)
+    const int* perm;            // [E] row of sh per edge (nullptr: identity)
+    const float* sh;
+    int sh_stride;
+    const int* seg_ptr;         // [n_out + 1]
+    const int* tile_node;       // [n_tiles + 1] first output node of every tile; tile_node[n_tiles] = n_out
+    const int* n_tiles_dev;     // device tile count (dynamic graphs) or nullptr
+    int n_tiles;
+    const float* oscale;
+    const float* oshift;
+    float* out;
+    const float* residual;
+    int res_dim, mode;
+    long long* dbg;             // profiling aid (PROBE instantiation only)
+};
+
+template <class Cfg>
+struct ConvFusedSmem {
+    static constexpr int XS = Cfg::D_IN | 1;                              // odd row strides: conflict-free thread-per-row access
+    static constexpr int OQ = ((Cfg::D_OUT + 3) / 4) | 1;                // float4 per staged row, odd: conflict-free STS.128 / LDS.128
+    static constexpr int OS = 4 * OQ;
+    static constexpr int ROW_FLOATS = XS > OS ? XS : OS;
+    static constexpr int X_BYTES = ((256 * ROW_FLOATS * 4 + 127) / 128) * 128;
+    static constexpr int TAIL = 2176;                                    // node_seg[257+], oscale/oshift, barriers, tmem slot
+    static constexpr int AVAIL = 227 * 1024 - X_BYTES - TAIL - 2 * CF_ALO_TILE;
+    static constexpr int STAGES = AVAIL / CF_B_STAGE > 6 ? 6 : AVAIL / CF_B_STAGE;
+    static constexpr int TOTAL = STAGES * CF_B_STAGE + 2 * CF_ALO_TILE + X_BYTES + TAIL;
+    static_assert(STAGES >= 3, "weight ring too small");
+};
+
+// TMEM -> registers, 16 (or 4) consecutive columns of this thread's lane
+__device__ __forceinline__ void cf_tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void cf_tmem_ld4(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+// wait for the outstanding tcgen05.ld; the registers are threaded through the asm so that no consumer can be
+// scheduled above the wait
+__device__ __forceinline__ void cf_wait_ld16(float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+// Converged-warp issue: every lane of the issuing warp executes these, one elected lane issues.  In uniform control flow
+// ptxas emits bare UTCHMMA / UTCBAR instructions; under `if (lane == 0)` it wraps each one in an ELECT / BRA.U.ANY loop
+// (~58 clk per MMA, measured), which starves the tensor pipe at N = 112 (56 clk per MMA).
+__device__ __forceinline__ void cf_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void cf_mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void cf_commit(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(tc_smem(bar))
+        : "memory");
+}
+// One warp-wide round trip for up to three barriers: lane 0 -> (b0, p0), lane 1 -> (b1, p1), lane 2 -> (b2, p2), the other
+// lanes shadow lane 0.  A barrier try_wait costs ~100 clk even when its phase is complete; the issuing warp's critical
+// path pays that once per weight chunk instead of three times.
+__device__ __forceinline__ void cf_wait3(uint64_t* b0, uint32_t p0, uint64_t* b1, uint32_t p1, uint64_t* b2, uint32_t p2, int lane) {
+    const uint32_t addr = tc_smem(lane == 1 ? b1 : (lane == 2 ? b2 : b0));
+    const uint32_t parity = lane == 1 ? p1 : (lane == 2 ? p2 : p0);
+#pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 28); ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (__all_sync(0xffffffffu, ok)) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void cf_bar_workers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// One 100-column chunk of path P (rows u0 .. u0 + 100/V - 1), this thread's edge.
+template <class Cfg, int P>
+__device__ __forceinline__ void cf_chunk(uint32_t tslot, const float* __restrict__ xrow, int u0, const float* shv,
+                                         float (&acc)[Cfg::D_OUT]) {
+    constexpr TpPath p = Cfg::paths[P];
+    constexpr TpOut o = Cfg::outs[p.oi];
+    constexpr int V = o.V, K = 2 * o.lo + 1, D1 = 2 * p.l1 + 1;
+    static_assert(CF_CHUNK % V == 0, "chunk must hold whole weight rows");
+    float wv[2][16];
+    float z[3] = {0.f, 0.f, 0.f};
+    cf_tmem_ld16(tslot, wv[0]);
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+        cf_wait_ld16(wv[q & 1]);
+        if (q + 1 < 6) cf_tmem_ld16(tslot + 16 * (q + 1), wv[(q + 1) & 1]);
+        else if (q + 1 == 6) cf_tmem_ld4(tslot + 96, wv[0]);
+#pragma unroll
+        for (int j = 0; j < (q < 6 ? 16 : 4); ++j) {
+            const int col = 16 * q + j, r = col / V, v = col % V;
+            if (v == 0) {                                                  // next weight row: Z[u, :] = CG(x[u, :], sh)
+                float xv[3];
+#pragma unroll
+                for (int i = 0; i < D1; ++i) xv[i] = xrow[p.in_off + (u0 + r) * D1 + i];
+                dp_cg<p.l1, p.l2, o.lo>(xv, shv + p.sh_off, z);
+            }
+            const float wj = wv[q & 1][j];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[o.off + v * K + k] = fmaf(wj, z[k], acc[o.off + v * K + k]);
+        }
+    }
+}
+
+template <class Cfg, int P, bool PROBE>
+__device__ __forceinline__ void cf_paths(uint32_t tmem_lane_base, uint64_t* t_full, uint64_t* t_empty, uint32_t& item, int tile,
+                                         int ntile, bool active, const float* __restrict__ xrow, const float* shv,
+                                         float (&acc)[Cfg::D_OUT], int lane, bool probe_on, uint32_t item0, long long* a_dbg) {
+    if constexpr (P < Cfg::NP) {
+        constexpr TpPath p = Cfg::paths[P];
+        constexpr int V = Cfg::outs[p.oi].V;
+        constexpr int NCH = p.U * V / CF_CHUNK, R = CF_CHUNK / V;
+        static_assert(p.U * V % CF_CHUNK == 0 && p.w_off % CF_CHUNK == 0, "path blocks must be multiples of the chunk");
+#pragma unroll 1
+        for (int j = 0; j < NCH; ++j) {
+            if (active) {
+                const uint32_t it = item, slot = 2 * (it & 1) + (uint32_t)tile, use = it >> 1;   // item: chunks drained by this thread so far
+                const bool st_on = probe_on && lane == 0 && (threadIdx.x >> 5 & 3) == 0;
+                if (st_on) CF_STAMP(1 + tile, it - item0, 0);
+                if (lane == 0) tc_mbar_wait(&t_full[slot], use & 1);       // one poller per warp keeps the barrier unit quiet
+                __syncwarp();
+                if (st_on) CF_STAMP(1 + tile, it - item0, 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                cf_chunk<Cfg, P>(tmem_lane_base + slot * CF_SLOT_COLS, xrow, j * R, shv, acc);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) tc_mbar_arrive(&t_empty[slot]);
+                if (st_on) CF_STAMP(1 + tile, it - item0, 2);
+            }
+            if (active) ++item;
+        }
+        cf_paths<Cfg, P + 1, PROBE>(tmem_lane_base, t_full, t_empty, item, tile, ntile, active, xrow, shv, acc, lane, probe_on, item0, a_dbg);
+    }
+}
+
+template <class Cfg, bool PROBE>
+__global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs a) {
+    long long* const a_dbg = a.dbg;
+    using S = ConvFusedSmem<Cfg>;
+    constexpr int NCH = Cfg::W / CF_CHUNK;
+    static_assert(Cfg::W % CF_CHUNK == 0, "W must be a multiple of the chunk");
+    extern __shared__ __align__(1024) uint8_t cf_smem_raw[];
+    uint8_t* b_st = cf_smem_raw;                                                    // STAGES x (hi | lo)
+    uint8_t* alo = b_st + S::STAGES * CF_B_STAGE;                                   // 2 tiles x [k/8][m/8][m%8][k%8] fp16 (A lo)
+    float* xs = reinterpret_cast<float*>(alo + 2 * CF_ALO_TILE);                    // [256][XS]; later [256][OS] staging
+    int* node_seg = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(xs) + S::X_BYTES);          // [<= 257] seg_ptr of the pair's nodes
+    float* osc = reinterpret_cast<float*>(node_seg + 260);                                        // oscale | oshift
+    float* osh = osc + Cfg::D_OUT;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(osc + 2 * 104);
+    uint64_t *b_full = bars, *b_empty = bars + S::STAGES, *t_full = bars + 2 * S::STAGES, *t_empty = t_full + CF_SLOTS,
+             *a_ready = t_empty + CF_SLOTS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // REDUX results live in uniform registers: everything derived from them (trip counts, the early exit, the MMA operands)
+    // is provably warp-uniform.  With the tile count or the TMEM base in vector registers ptxas treats the issuing warp as
+    // possibly divergent and brackets every UTCHMMA with ELECT / R2UR / VOTEU sequences that cost as much as the MMA itself.
+    const int n_tiles = __reduce_max_sync(0xffffffffu, a.n_tiles_dev ? *a.n_tiles_dev : a.n_tiles);
+    const int n_pairs = (n_tiles + 1) >> 1;
+    if ((int)blockIdx.x >= n_pairs) return;
+    const int my_pairs = (n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (tid == 0) {
+        for (int i = 0; i < S::STAGES; ++i) { tc_mbar_init(&b_full[i], 1); tc_mbar_init(&b_empty[i], 2); }
+        for (int i = 0; i < CF_SLOTS; ++i) { tc_mbar_init(&t_full[i], 1); tc_mbar_init(&t_empty[i], 4); }
+        tc_mbar_init(a_ready, CF_WORKERS / 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < Cfg::D_OUT; i += CF_THREADS) { osc[i] = a.oscale[i]; osh[i] = a.oshift[i]; }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tc_smem(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, *tmem_slot);
+
+    if (warp == 10) {
+        // ================= TMA producer (one thread): the weight chunks cycle through the ring, pair after pair =================
+        if (lane == 0) {
+            const uint32_t total_chunks = (uint32_t)my_pairs * NCH;
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w2img);
+            for (uint32_t g = 0; g < total_chunks; ++g) {
+                const uint32_t s = g % S::STAGES, u = g / S::STAGES;
+                tc_mbar_wait(&b_empty[s], (u & 1) ^ 1);
+                tc_mbar_expect_tx(&b_full[s], CF_B_STAGE);
+                tc_bulk_load(b_st + s * CF_B_STAGE, wsrc + (size_t)(g % NCH) * CF_B_STAGE, CF_B_STAGE, &b_full[s]);
+            }
+        }
+    } else if (warp >= 8) {
+        // ================= MMA issuers: warp 8 -> tile 0 (accumulator slots 0, 2), warp 9 -> tile 1 (slots 1, 3).
+        // One issuing warp needs ~55 clk of instructions per UTCHMMA, about the 56 clk an M=128, N=112, K=16 MMA occupies
+        // the tensor pipe, so every barrier round trip of a single issuer would starve the pipe; two issuers hide each
+        // other's waits.  Each (slot, barrier) pair has exactly one producer and one consumer group, so every parity wait
+        // stays within one phase of its barrier. =================
+        {
+            const int t = warp - 8;
+            // instruction descriptor: D = F32, A = B = F16, K-major, N = 112, M = 128
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(CF_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t b_base = tc_smem(b_st);
+            const uint32_t a_hi_t = tmem_base + CF_A_COL + (uint32_t)(t * 32);
+            const uint32_t a_lo_s = tc_smem(alo) + (uint32_t)(t * CF_ALO_TILE);
+            uint32_t g = 0, use = 0;                                        // use: items issued by this warp so far
+            for (int pi = 0; pi < my_pairs; ++pi) {
+                const int pair = (int)blockIdx.x + pi * (int)gridDim.x;
+                const int ntile = (2 * pair + 1 < n_tiles) ? 2 : 1;
+                const bool mine = t < ntile;
+                const bool probe_on = pi == 1 && lane == 0 && t == 0;
+                int pidx = 0;
+                // A operands of this pair are in place (vote-terminated waits: the warp provably stays converged)
+                cf_wait3(a_ready, (uint32_t)(pi & 1), a_ready, (uint32_t)(pi & 1), a_ready, (uint32_t)(pi & 1), lane);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // barriers of one chunk: its weights landed, this tile's accumulator slot is drained
+                auto wait_chunk = [&](uint32_t gg, uint32_t uu) {
+                    uint64_t* te = &t_empty[2 * (uu & 1) + t];
+                    const uint32_t tp = ((uu >> 1) & 1) ^ 1;
+                    cf_wait3(&b_full[gg % S::STAGES], (gg / S::STAGES) & 1, mine ? te : &b_full[gg % S::STAGES],
+                             mine ? tp : (gg / S::STAGES) & 1, &b_full[gg % S::STAGES], (gg / S::STAGES) & 1, lane);
+                };
+                CF_STAMP(0, 0, 0);
+                wait_chunk(g, use);
+                for (int c = 0; c < NCH; ++c, ++g) {
+                    const uint32_t s = g % S::STAGES;
+                    if (!mine) {                                            // single-tile pair: only release the weight stage
+                        if (lane == 0) tc_mbar_arrive(&b_empty[s]);
+                        __syncwarp();
+                        if (c + 1 < NCH) wait_chunk(g + 1, use);
+                        continue;
+                    }
+                    CF_STAMP(0, pidx, 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t b_hi_s = b_base + s * CF_B_STAGE, b_lo_s = b_hi_s + CF_B_HALF;
+                    const uint32_t slot = 2 * (use & 1) + (uint32_t)t;
+                    const uint32_t d = tmem_base + slot * CF_SLOT_COLS;
+#pragma unroll
+                    for (int combo = 0; combo < 3; ++combo) {              // hi*hi + hi*lo (A from TMEM) + lo*hi (A from smem)
+                        const uint32_t bs = combo == 1 ? b_lo_s : b_hi_s;
+                        if (combo == 2 && c + 1 < NCH) {
+                            // the next chunk's barrier round trip hides behind the MMAs queued so far
+                            CF_STAMP(0, pidx + 1, 0);
+                            wait_chunk(g + 1, use + 1);
+                        }
+#pragma unroll
+                        for (int ks = 0; ks < TC_K / 16; ++ks) {
+                            // fp16 K-major no-swizzle: core matrix = 8 rows x 8 halfs (128 B); B: 14 row groups per K chunk,
+                            // A lo: 16 row groups per K chunk
+                            const uint64_t bd = tc_smem_desc(bs + ks * 2 * (CF_N * 16), CF_N * 16, 128);
+                            if (combo < 2) cf_mma_f16_ts(d, a_hi_t + (uint32_t)(ks * 8), bd, idesc, (combo | ks) ? 1u : 0u);
+                            else cf_mma_f16_ss(d, tc_smem_desc(a_lo_s + ks * 2 * 2048, 2048, 128), bd, idesc, 1u);
+                        }
+                    }
+                    cf_commit(&t_full[slot]);
+                    cf_commit(&b_empty[s]);
+                    CF_STAMP(0, pidx, 2);
+                    ++pidx;
+                    ++use;
+                }
+            }
+        }
+    } else {
+        // ================= workers: thread = edge =================
+        const int tile = warp >> 2, wq = warp & 3, row = wq * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
+        float* xrow = xs + (size_t)tid * S::XS;
+        uint32_t item = 0;
+        // indices of this thread's edge in pair `pr`: node range of the pair, first edge / edge count of its tile, gathered
+        // node row, SH row
+        struct Idx { int n_lo, n_mid, n_hi, eb, ne, src, ce; };
+        auto fetch = [&](int pr) {
+            Idx x;
+            const int T0 = 2 * pr, nt = (T0 + 1 < n_tiles) ? 2 : 1;
+            x.n_lo = a.tile_node[T0]; x.n_mid = a.tile_node[T0 + 1]; x.n_hi = a.tile_node[T0 + nt];
+            x.eb = 0; x.ne = 0; x.src = -1; x.ce = 0;
+            if (tile < nt) {
+                x.eb = a.seg_ptr[tile ? x.n_mid : x.n_lo];
+                x.ne = a.seg_ptr[tile ? x.n_hi : x.n_mid] - x.eb;
+                if (row < x.ne) {
+                    x.src = a.gather_idx ? a.gather_idx[x.eb + row] : x.eb + row;
+                    x.ce = a.perm ? a.perm[x.eb + row] : x.eb + row;
+                }
+            }
+            return x;
+        };
+        Idx ix = fetch((int)blockIdx.x);
+        for (int pi = 0; pi < my_pairs; ++pi) {
+            const int pair = (int)blockIdx.x + pi * (int)gridDim.x;
+            const int ntile = (2 * pair + 1 < n_tiles) ? 2 : 1;
+            const bool active = tile < ntile;
+            if (ix.ne > 128) __trap();                                       // tile builder contract violated
+            const bool valid = row < ix.ne;
+            const int e = ix.eb + row;
+            const bool probe_on = pi == 1 && tid == 0;
+            CF_STAMP(1, 50, 0);
+            float shv[Cfg::SH_USED];
+            // ---- prologue 1: A operands -> TMEM (the MMAs of this pair can start as soon as they are there) ----
+            float rs = 0.f;
+            if (active) {
+                float h[64];
+                float m = 1.0f;
+                if (valid) {
+                    // edge-interleaved layout written by edge_hidden_kernel: [e / 32][16 quads][e % 32][4]
+                    const float4* hp = reinterpret_cast<const float4*>(a.himg) + (size_t)(e >> 5) * 512 + (e & 31);
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const float4 v = __ldg(hp + q * 32);
+                        h[4 * q] = v.x; h[4 * q + 1] = v.y; h[4 * q + 2] = v.z; h[4 * q + 3] = v.w;
+                        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 64; ++q) h[q] = 0.f;
+                }
+                // s = 2^(12 - floor(log2 m)): m * s in [2^12, 2^13); m >= 1 (the bias column holds 1.0)
+                const int ex = (int)((__float_as_uint(m) >> 23) & 0xFF) - 127;
+                const float sc = __uint_as_float((uint32_t)(127 + 12 - ex) << 23);
+                rs = __uint_as_float((uint32_t)(127 - 12 + ex) << 23) * a.inv_wscale;
+                uint32_t hi_p[32], lo_p[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const float x0 = h[2 * c] * sc, x1 = h[2 * c + 1] * sc;
+                    const __half2 hh = __floats2half2_rn(x0, x1);           // packed conversions (F2FP), 2 values per instruction
+                    const float2 hf = __half22float2(hh);
+                    const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                    hi_p[c] = *reinterpret_cast<const uint32_t*>(&hh);
+                    lo_p[c] = *reinterpret_cast<const uint32_t*>(&ll);
+                }
+                tc_tmem_st32(lane_base + CF_A_COL + (uint32_t)(tile * 32), hi_p);
+                // lo part: K-major core matrices [k/8][m/8][m%8][k%8]; 8 consecutive rows write 128 contiguous bytes
+                uint8_t* lo_dst = alo + tile * CF_ALO_TILE + (row >> 3) * 128 + (row & 7) * 16;
+#pragma unroll
+                for (int kc = 0; kc < 8; ++kc)
+                    *reinterpret_cast<uint4*>(lo_dst + kc * 2048) = make_uint4(lo_p[4 * kc], lo_p[4 * kc + 1], lo_p[4 * kc + 2], lo_p[4 * kc + 3]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> tensor-core (async proxy) reads
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(a_ready);
+            CF_STAMP(1, 50, 1);
+            // ---- prologue 2 (under the first MMAs): gathered node rows -> smem (warp-cooperative, coalesced), SH -> registers,
+            //      seg_ptr of the pair's nodes -> smem for the epilogue ----
+            for (int i = tid; i <= ix.n_hi - ix.n_lo; i += CF_WORKERS) node_seg[i] = a.seg_ptr[ix.n_lo + i];
+            if (active) {
+                constexpr int NC = (Cfg::D_IN + 31) / 32;
+#pragma unroll 1
+                for (int r0 = 0; r0 < 32; r0 += CF_XB) {                      // CF_XB rows = up to 4 CF_XB coalesced loads in flight
+                    float v[CF_XB][NC];
+#pragma unroll
+                    for (int j = 0; j < CF_XB; ++j) {
+                        const int sr = __shfl_sync(0xffffffffu, ix.src, r0 + j);
+                        const float* srow = a.node_in + (size_t)(sr < 0 ? 0 : sr) * Cfg::D_IN;
+#pragma unroll
+                        for (int k = 0; k < NC; ++k) {
+                            const int c = 32 * k + lane;
+                            v[j][k] = (sr >= 0 && c < Cfg::D_IN) ? __ldg(srow + c) : 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < CF_XB; ++j) {
+                        float* dst = xs + (size_t)(tid - lane + r0 + j) * S::XS;
+#pragma unroll
+                        for (int k = 0; k < NC; ++k) {
+                            const int c = 32 * k + lane;
+                            if (c < Cfg::D_IN) dst[c] = v[j][k];
+                        }
+                    }
+                }
+                // the power-of-two operand scales are undone exactly by scaling the spherical harmonics (Z is linear in them)
+#pragma unroll
+                for (int i = 0; i < Cfg::SH_USED; ++i) shv[i] = valid ? __ldg(a.sh + (size_t)ix.ce * a.sh_stride + i) * rs : 0.f;
+            } else {
+#pragma unroll
+                for (int i = 0; i < Cfg::SH_USED; ++i) shv[i] = 0.f;
+            }
+            __syncwarp();
+            // indices of the next pair: their round trips hide behind the main loop
+            Idx nx = ix;
+            if (pi + 1 < my_pairs) nx = fetch(pair + (int)gridDim.x);
+            // ---- main loop: weights from TMEM, contraction on CUDA cores ----
+            float acc[Cfg::D_OUT];
+#pragma unroll
+            for (int d = 0; d < Cfg::D_OUT; ++d) acc[d] = 0.f;
+            cf_paths<Cfg, 0, PROBE>(lane_base, t_full, t_empty, item, tile, ntile, active, xrow, shv, acc, lane, pi == 1, item, a_dbg);
+            CF_STAMP(1, 50, 2);
+            // ---- epilogue: per-edge results -> smem (aliases the node rows), segmented mean + BatchNorm + residual ----
+            cf_bar_workers();                                              // every worker is done with its node row
+            float* stg = xs;
+            if (active) {
+#pragma unroll
+                for (int q = 0; q < S::OQ; ++q) {
+                    float4 v;
+                    v.x = 4 * q < Cfg::D_OUT ? acc[4 * q < Cfg::D_OUT ? 4 * q : 0] : 0.f;
+                    v.y = 4 * q + 1 < Cfg::D_OUT ? acc[4 * q + 1 < Cfg::D_OUT ? 4 * q + 1 : 0] : 0.f;
+                    v.z = 4 * q + 2 < Cfg::D_OUT ? acc[4 * q + 2 < Cfg::D_OUT ? 4 * q + 2 : 0] : 0.f;
+                    v.w = 4 * q + 3 < Cfg::D_OUT ? acc[4 * q + 3 < Cfg::D_OUT ? 4 * q + 3 : 0] : 0.f;
+                    *reinterpret_cast<float4*>(stg + (size_t)tid * S::OS + 4 * q) = v;
+                }
+            }
+            cf_bar_workers();
+            CF_STAMP(1, 51, 0);
+            {
+                const int e_lo = node_seg[0], e_mid = node_seg[ix.n_mid - ix.n_lo];
+                const int items = (ix.n_hi - ix.n_lo) * S::OQ;
+                for (int it = tid; it < items; it += CF_WORKERS) {
+                    const int nl = it / S::OQ, q = it % S::OQ, node = ix.n_lo + nl;
+                    const int s0 = node_seg[nl], s1 = node_seg[nl + 1];
+                    float* orow = a.out + (size_t)node * Cfg::D_OUT;
+                    float add[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {                            // residual / running sum: loads overlap the reduction
+                        const int d = 4 * q + j;
+                        add[j] = 0.f;
+                        if (d < Cfg::D_OUT) {
+                            if (a.mode == 1) add[j] = (d < a.res_dim) ? a.residual[(size_t)node * a.res_dim + d] : 0.0f;
+                            else if (a.mode == 2) add[j] = orow[d];
+                        }
+                    }
+                    const int r0 = node < ix.n_mid ? s0 - e_lo : 128 + s0 - e_mid;
+                    const float* sp = stg + (size_t)r0 * S::OS + 4 * q;
+                    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+                    for (int r = 0; r < s1 - s0; ++r) {                      // sequential in edge order: composition-invariant
+                        const float4 v = *reinterpret_cast<const float4*>(sp + (size_t)r * S::OS);
+                        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                    }
+                    const int deg = s1 - s0;
+                    const float inv_deg = 1.0f / (float)(deg > 0 ? deg : 1);
+                    const float sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int d = 4 * q + j;
+                        if (d < Cfg::D_OUT) orow[d] = sv[j] * inv_deg * osc[d] + osh[d] + add[j];
+                    }
+                }
+            }
+            CF_STAMP(1, 51, 1);
+            cf_bar_workers();                                              // staging is free before the next pair's rows land
+            CF_STAMP(1, 51, 2);
+            ix = nx;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 8) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+template <class Cfg>
+static int conv_fused_launch(const ConvFusedArgs& a, cudaStream_t st) {
+    if (a.n_tiles <= 0) return DP_OK;
+    using S = ConvFusedSmem<Cfg>;
+    static bool attr_set = false;
+    static int n_sm = 0;
+    auto kern = conv_fused_kernel<Cfg, false>;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
+            return dp_check_launch("dp_conv_fused(attr)");
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        attr_set = true;
+    }
+    const int n_pairs = (a.n_tiles + 1) / 2;
+    const int grid = n_pairs < n_sm ? n_pairs : n_sm;
+    if constexpr (Cfg::W == 2200) {
+        if (a.dbg) {                                                       // profiling aid (tools/conv_fused_probe.py --stamps)
+            auto pk = conv_fused_kernel<Cfg, true>;
+            cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+            pk<<<grid, CF_THREADS, S::TOTAL, st>>>(a);
+            return dp_check_launch("dp_conv_fused(probe)");
+        }
+    }
+    kern<<<grid, CF_THREADS, S::TOTAL, st>>>(a);
+    return dp_check_launch("dp_conv_fused");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tile builder for dynamic graphs: greedy node-aligned packing (<= 128 edges per tile), restarted at every graph so
+// that graphs can be processed in parallel (one thread per graph), two passes around the exclusive scan.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void tile_count_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ node_ptr, int n_graphs,
+                                  int* __restrict__ cnt) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_graphs) return;
+    const int n0 = node_ptr[g], n1 = node_ptr[g + 1];
+    int tiles = 0, fill = 0;
+    bool open = false;
+    for (int n = n0; n < n1; ++n) {
+        const int d = seg_ptr[n + 1] - seg_ptr[n];
+        if (!open || fill + d > 128) { ++tiles; fill = 0; open = true; }
+        fill += d;
+    }
+    cnt[g] = tiles;
+}
+__global__ void tile_fill_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ node_ptr, int n_graphs,
+                                 const int* __restrict__ start, int* __restrict__ tile_node) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_graphs) return;
+    const int n0 = node_ptr[g], n1 = node_ptr[g + 1];
+    int t = start[g], fill = 0;
+    bool open = false;
+    for (int n = n0; n < n1; ++n) {
+        const int d = seg_ptr[n + 1] - seg_ptr[n];
+        if (!open || fill + d > 128) { tile_node[t++] = n; fill = 0; open = true; }
+        fill += d;
+    }
+    if (g == n_graphs - 1) tile_node[start[n_graphs]] = n1;              // sentinel: one past the last node
+}

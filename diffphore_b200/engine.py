@@ -54,10 +54,14 @@ class ConvWeights:
         self.w1 = _f32(sd[prefix + '.fc.0.weight']).to(device)
         self.b1 = _f32(sd[prefix + '.fc.0.bias']).to(device)
         self.w2t = torch.cat([_f32(w3).T, _f32(sd[prefix + '.fc.3.bias'])[None, :]], 0).contiguous().to(device)
-        self.w2img, self.inv_wscale = None, 1.0
+        self.w2img, self.inv_wscale, self.w2img112 = None, 1.0, None
         if self.hid == 60 and self.in_dim == 60:
             img, self.inv_wscale = self.make_w2img(_f32(w3).cpu(), _f32(sd[prefix + '.fc.3.bias']).cpu())
             self.w2img = img.to(device)
+            if numel % 100 == 0:
+                img, s112 = _make_w2img112(_f32(w3).cpu(), _f32(sd[prefix + '.fc.3.bias']).cpu())
+                assert s112 == self.inv_wscale
+                self.w2img112 = img.to(device)
         # eval BatchNorm (e3nn.nn.BatchNorm) and path weights folded into per-component scale/shift
         bw, bb = sd[prefix + '.batch_norm.weight'].double(), sd[prefix + '.batch_norm.bias'].double()
         rm, rv = sd[prefix + '.batch_norm.running_mean'].double(), sd[prefix + '.batch_norm.running_var'].double()
@@ -79,6 +83,8 @@ class ConvWeights:
         self.oscale = torch.cat(scale).float().contiguous().to(device)
         self.oshift = torch.cat(shift).float().contiguous().to(device)
         self.d_in, self.d_out = irreps_dim(in_irreps), irreps_dim(out_irreps)
+        # channel-mixing FLOPs per edge of the tensor product: sum over paths 2 * mul_in * mul_out * (2 l_out + 1)
+        self.tp_flops = sum(2 * in_irreps[i.i1][0] * out_irreps[i.io][0] * (2 * out_irreps[i.io][1] + 1) for i in instrs)
 
 
 def _make_w2img(w3, b3):
@@ -99,6 +105,41 @@ def _make_w2img(w3, b3):
     lo = (xs - hi.float()).half()
     img = torch.stack([hi, lo], 0).reshape(2, nch, 8, 8, 8, 8).permute(1, 0, 4, 2, 3, 5)       # [c][h][kc][ng][r][j]
     return img.contiguous().reshape(-1).view(torch.uint8), 2.0 ** (-k)
+
+
+def _make_w2img112(w3, b3):
+    """Shared-memory image of the second-layer weights for dp_conv_fused: like _make_w2img, but per 100-column chunk of
+    the e3nn weight layout, zero padded to the MMA N of 112: [chunk][hi|lo][k/8][n/8 (14)][n%8][k%8] fp16.
+    Returns (uint8 image tensor, 2^-k)."""
+    W = w3.shape[0]
+    assert W % 100 == 0
+    nch = W // 100
+    x = torch.zeros(nch, 112, 64, dtype=torch.float32)
+    x[:, :100, :60] = w3.reshape(nch, 100, 60)
+    x[:, :100, 60] = b3.reshape(nch, 100)
+    m = float(x.abs().max())
+    k = 12 - math.floor(math.log2(m)) if m > 0 and math.isfinite(m) else 0
+    xs = x * (2.0 ** k)
+    hi = xs.half()
+    lo = (xs - hi.float()).half()
+    img = torch.stack([hi, lo], 1).reshape(nch, 2, 14, 8, 8, 8).permute(0, 1, 4, 2, 3, 5)     # [c][h][kc][ng][r][j]
+    return img.contiguous().reshape(-1).view(torch.uint8), 2.0 ** (-k)
+
+
+def greedy_tiles(deg, cap=128):
+    """Node-aligned tiles for dp_conv_fused: runs of whole output nodes with <= cap edges (same rule as
+    tile_count_kernel / tile_fill_kernel).  deg: per-node edge counts of ONE graph.  Returns the first node of every
+    tile, or None if a single node exceeds the cap."""
+    first, fill = [], 0
+    for n, d in enumerate(deg):
+        d = int(d)
+        if d > cap:
+            return None
+        if not first or fill + d > cap:
+            first.append(n)
+            fill = 0
+        fill += d
+    return first
 
 
 class ModelWeights:
@@ -274,9 +315,14 @@ class PackedBatch:
         cl, cp, cptr, masks, moff = [], [], [0], [], [0]
         cl_t, cp_t, perm_t, cseg_ph = [], [], [], [0]
         e_off = pp_off = c_off = 0
+        tl_lig, tl_ph, tl_pp = [], [], []          # node-aligned tiles of the static edge sets (dp_conv_fused)
         for p in pa:
+            t_lig, t_ph = greedy_tiles([p.P] * p.n), greedy_tiles([p.n] * p.P)
+            t_pp = greedy_tiles(np.diff(p.pp_ptr))
             for s in range(S):
                 a0, p0 = int(lig_ptr[gi]), int(ph_ptr[gi])
+                for lst, t, off in ((tl_lig, t_lig, a0), (tl_ph, t_ph, p0), (tl_pp, t_pp, p0)):
+                    lst.append(None if t is None else np.asarray(t, np.int64) + off)
                 bond_ptr.append(p.bond_ptr[:-1] + e_off)
                 bond_dst.append(p.bond_dst + a0)
                 bond_type.append(p.bond_type)
@@ -329,6 +375,14 @@ class PackedBatch:
         # CSR of cross edges by ligand atom (canonical order) and by phore node (transposed order)
         self.cross_seg_lig = i32(np.concatenate([[0], np.cumsum(np.repeat(P_per, n_per))]))
         self.cross_seg_ph = i32(np.concatenate([[0], np.cumsum(np.repeat(n_per, P_per))]))
+        def tiles(lst, n_nodes):
+            if any(t is None for t in lst):
+                return None                     # a node with > 128 edges: this edge set stays on the unfused kernels
+            t = np.concatenate(lst + [np.asarray([n_nodes], np.int64)])
+            return (i32(t), None, len(t) - 1)
+
+        self.tiles_cross_lig, self.tiles_cross_ph = tiles(tl_lig, self.n_lig), tiles(tl_ph, self.n_ph)
+        self.tiles_pp = tiles(tl_pp, self.n_ph)
         self.mask = up(torch.from_numpy(cat(masks, np.uint8)))
         self.mask_off = up(torch.from_numpy(np.asarray(moff[:-1], dtype=np.int64)))
         self.lig_arange = torch.arange(self.n_lig, dtype=torch.int32, device=device)
@@ -380,6 +434,11 @@ class Workspace:
         max_edges = max(b.ll_cap, b.n_cross, b.n_pp, b.tor_cap, 1)
         self.hbuf = f(((max_edges + 127) // 128) * 128 * 64)          # hidden activations of dp_edge_mlp_tc (pass 1 -> pass 2)
         self.wbuf = wbuf if wbuf is not None and wbuf.numel() >= w_elems else f(w_elems)   # per-edge TP weights
+        # node-aligned tiles of the dynamic edge sets (dp_build_tiles): <= 2 E / 128 + 1 tiles per graph
+        self.tile_cnt, self.tile_start = i(b.B), i(b.B + 1)
+        self.ll_tile_cap, self.tor_tile_cap = b.ll_cap // 64 + b.B, b.tor_cap // 64 + b.B
+        self.ll_tiles, self.ll_ntiles = i(self.ll_tile_cap + 1), i(1)
+        self.tor_tiles, self.tor_ntiles = i(self.tor_tile_cap + 1), i(1)
         self.n_launches = 0
 
 
@@ -393,6 +452,10 @@ class Engine:
         # second MLP layer on tcgen05 tensor cores (3xTF32) or on CUDA cores (FFMA); env DIFFPHORE_EDGE_MLP=ffma|tc
         import os
         self.use_tc = os.environ.get('DIFFPHORE_EDGE_MLP', 'tc') == 'tc'
+        # DIFFPHORE_CONV=fused (default): dp_edge_hidden + dp_conv_fused, the per-edge weights never leave the SM;
+        # DIFFPHORE_CONV=split: dp_edge_mlp(_tc) -> HBM -> dp_tp_scatter (kept for A/B measurements and as the path for
+        # edge sets the fused kernel does not cover: hid != 60, W % 100 != 0, nodes with more than 128 edges)
+        self.use_fused = os.environ.get('DIFFPHORE_CONV', 'fused') == 'fused'
 
     def pack(self, graphs, samples_per_graph=1, wbuf=None):
         """Upload a batch and run the static-geometry setup kernels.  wbuf: optional shared per-edge weight buffer
@@ -409,7 +472,7 @@ class Engine:
 
     # ------------------------------------------------------------------ one TensorProductConvLayer
     def _conv(self, cw, ws, emb, perm, tb, idxB, tc, idxC, idxC2, n_dev, n_cap, node_in, gather, sh, sh_stride, seg, out,
-              residual, res_dim, mode, n_out, st, name=''):
+              residual, res_dim, mode, n_out, st, name='', tiles=None):
         p = L.ptr
         tm = self.timer
         if tm is not None:
@@ -418,6 +481,21 @@ class Engine:
                 n_rec = torch.empty(1, dtype=torch.int32).pin_memory()
                 n_rec.copy_(n_dev, non_blocking=True)
             e0 = tm.start()
+        if self.use_fused and tiles is not None and cw.w2img112 is not None:
+            tile_node, n_tiles_dev, n_tiles_cap = tiles
+            L.check(self.lib.dp_edge_hidden(p(emb), p(perm), p(tb), p(idxB), tb.shape[1], p(tc), p(idxC), p(idxC2), tc.shape[1],
+                                            p(cw.w1), p(cw.b1), p(n_dev), n_cap, p(ws.hbuf), st), 'dp_edge_hidden')
+            if tm is not None:
+                tm.stop('edge_hidden', name, e0, n_rec, dict(in_dim=cw.in_dim, hid=cw.hid, W=0))
+                e0 = tm.start()
+            L.check(self.lib.dp_conv_fused(cw.layer_id, p(ws.hbuf), p(cw.w2img112), cw.inv_wscale, p(node_in), p(gather), p(perm),
+                                           p(sh), sh_stride, p(seg), p(tile_node), p(n_tiles_dev), n_tiles_cap, p(cw.oscale),
+                                           p(cw.oshift), p(out), p(residual), res_dim, mode, st), 'dp_conv_fused')
+            if tm is not None:
+                tm.stop('conv_fused', name, e0, n_rec, dict(W=cw.W, hid=cw.hid, d_in=cw.d_in, d_out=cw.d_out, n_out=n_out,
+                                                            tp_flops=cw.tp_flops))
+            ws.n_launches += 2
+            return
         if self.use_tc and cw.w2img is not None:
             L.check(self.lib.dp_edge_mlp_tc(p(emb), p(perm), p(tb), p(idxB), tb.shape[1], p(tc), p(idxC), p(idxC2), tc.shape[1],
                                             p(cw.w1), p(cw.b1), p(cw.w2img), cw.inv_wscale, cw.in_dim, cw.hid, cw.W, p(n_dev),
@@ -454,26 +532,34 @@ class Engine:
                                   p(ws.cross_fm), sw, scp, p(ws.cross_tw), p(ws.cross_emb), p(ws.cross_sh),
                                   p(ws.cross_nsh), st), 'dp_cross_step')
         ws.n_launches += 6
+        ll_tiles = None
+        if self.use_fused:
+            L.check(lib.dp_build_tiles(p(ws.ll_ptr), p(b.lig_ptr), b.B, p(ws.tile_cnt), p(ws.tile_start), p(ws.ll_tiles),
+                                       p(ws.ll_ntiles), st), 'dp_build_tiles')
+            ws.n_launches += 3
+            ll_tiles = (ws.ll_tiles, ws.ll_ntiles, ws.ll_tile_cap)
         cv = self.w.convs
         for l in range(4):
             lh, ph, lo = ws.lig_h[l], ws.ph_h[l] if l < 4 else None, ws.lig_h[l + 1]
             d = LAYER_DIMS[l]
             self._conv(cv[('lig', l)], ws, ws.ll_emb, None, lh, ws.ll_src, lh, ws.ll_dst, None, ws.ll_n, b.ll_cap,
-                       lh, ws.ll_dst, ws.ll_sh, 9, ws.ll_ptr, lo, lh, d, 1, b.n_lig, st, f'lig{l}')
+                       lh, ws.ll_dst, ws.ll_sh, 9, ws.ll_ptr, lo, lh, d, 1, b.n_lig, st, f'lig{l}', ll_tiles)
             self._conv(cv[('phore_to_lig', l)], ws, ws.cross_emb, None, lh, b.cross_lig, ph, b.cross_ph, None, None,
-                       b.n_cross, ph, b.cross_ph, ws.cross_sh, 9, b.cross_seg_lig, lo, None, 0, 2, b.n_lig, st, f'p2l{l}')
+                       b.n_cross, ph, b.cross_ph, ws.cross_sh, 9, b.cross_seg_lig, lo, None, 0, 2, b.n_lig, st, f'p2l{l}',
+                       b.tiles_cross_lig)
             self._conv(cv[('phore_to_lig_norm', l)], ws, ws.cross_emb, None, lh, b.cross_lig, ph, b.cross_ph, None, None,
-                       b.n_cross, ph, b.cross_ph, ws.cross_nsh, 9, b.cross_seg_lig, lo, None, 0, 2, b.n_lig, st, f'p2ln{l}')
+                       b.n_cross, ph, b.cross_ph, ws.cross_nsh, 9, b.cross_seg_lig, lo, None, 0, 2, b.n_lig, st, f'p2ln{l}',
+                       b.tiles_cross_lig)
             if l != 3:
                 po = ws.ph_h[l + 1]
                 self._conv(cv[('phore', l)], ws, ws.pp_emb, None, ph, b.pp_src, ph, b.pp_dst, None, None, b.n_pp,
-                           ph, b.pp_dst, ws.pp_sh, 9, b.pp_ptr, po, ph, d, 1, b.n_ph, st, f'pp{l}')
+                           ph, b.pp_dst, ws.pp_sh, 9, b.pp_ptr, po, ph, d, 1, b.n_ph, st, f'pp{l}', b.tiles_pp)
                 self._conv(cv[('lig_to_phore', l)], ws, ws.cross_emb, b.cross_perm_t, lh, b.cross_lig_t, ph, b.cross_ph_t,
                            None, None, b.n_cross, lh, b.cross_lig_t, ws.cross_sh, 9, b.cross_seg_ph, po, None, 0, 2,
-                           b.n_ph, st, f'l2p{l}')
+                           b.n_ph, st, f'l2p{l}', b.tiles_cross_ph)
                 self._conv(cv[('lig_to_phore_norm', l)], ws, ws.cross_emb, b.cross_perm_t, lh, b.cross_lig_t, ph,
                            b.cross_ph_t, None, None, b.n_cross, lh, b.cross_lig_t, ws.cross_nsh, 9, b.cross_seg_ph, po,
-                           None, 0, 2, b.n_ph, st, f'l2pn{l}')
+                           None, 0, 2, b.n_ph, st, f'l2pn{l}', b.tiles_cross_ph)
         h4 = ws.lig_h[4]
         L.check(lib.dp_center_step(p(b.pos), p(b.lig_ptr), b.B, sw, scp, p(ws.c_emb), p(ws.c_sh), st), 'dp_center_step')
         self._conv(cv['final'], ws, ws.c_emb, None, h4, b.lig_arange, None, None, None, None, b.n_lig, h4, None, ws.c_sh, 9,
@@ -484,8 +570,14 @@ class Engine:
             L.check(lib.dp_tor_graph(p(b.pos), p(b.lig_ptr), p(b.rot_ptr), p(b.rot_u), p(b.rot_v), b.B, b.n_rot, sw,
                                      p(ws.deg), p(ws.gcount), p(ws.gstart), p(ws.t_ptr), p(ws.t_atom), p(ws.t_u), p(ws.t_v),
                                      p(ws.t_emb), p(ws.t_sh), p(ws.t_n), st), 'dp_tor_graph')
+            tor_tiles = None
+            if self.use_fused:
+                L.check(lib.dp_build_tiles(p(ws.t_ptr), p(b.rot_ptr), b.B, p(ws.tile_cnt), p(ws.tile_start), p(ws.tor_tiles),
+                                           p(ws.tor_ntiles), st), 'dp_build_tiles')
+                ws.n_launches += 3
+                tor_tiles = (ws.tor_tiles, ws.tor_ntiles, ws.tor_tile_cap)
             self._conv(cv['tor'], ws, ws.t_emb, None, h4, ws.t_atom, h4, ws.t_u, ws.t_v, ws.t_n, b.tor_cap, h4, ws.t_atom,
-                       ws.t_sh, 8, ws.t_ptr, ws.tor_feat, None, 0, 0, b.n_rot, st, 'tor')
+                       ws.t_sh, 8, ws.t_ptr, ws.tor_feat, None, 0, 0, b.n_rot, st, 'tor', tor_tiles)
             L.check(lib.dp_tor_head(p(ws.tor_feat), b.n_rot, sw, scp, p(ws.tor), st), 'dp_tor_head')
             ws.n_launches += 4
         return ws.tr, ws.rot, ws.tor[:b.n_rot]
