@@ -36,6 +36,7 @@
 #define CF_SLOTS 4                                    // accumulator slots (TMEM), rotating over the (chunk, tile) items
 #define CF_SLOT_COLS 112
 #define CF_A_COL 448                                  // A hi operands: tile t -> TMEM columns 448 + 32 t
+#define CF_W1_BYTES (2 * 64 * TC_K * 2)               // hi | lo image of the first-layer weights (N = 64): 16 KB, one ring stage
 #define CF_ALO_TILE (128 * TC_K * 2)                  // A lo operand of one tile in shared memory (K-major core matrices): 16 KB
 
 // profiling aid (tools/conv_fused_probe.py --stamps): clock64() stamps of CTA 0, second pair; role 0 = MMA issuer,
@@ -43,7 +44,17 @@
 #define CF_STAMP(role, idx, k) do { if (PROBE && blockIdx.x == 0 && probe_on && (idx) < 64) a_dbg[((role) * 64 + (idx)) * 3 + (k)] = clock64(); } while (0)
 
 struct ConvFusedArgs {
-    const float* himg;          // [E][64] hidden activations (edge_hidden_kernel), edge order = seg order
+    // first MLP layer: attr(e) = [emb[perm[e]] | tb[idxB[e], 0:20] | tc[idxC[e], 0:20] (+ tc[idxC2[e], 0:20])]
+    const float* emb;           // [E_canonical, 20] edge embedding
+    const float* tb;            // node table of part B, row stride strideB floats
+    const int* idxB;
+    int strideB;
+    const float* tc;            // node table of part C
+    const int* idxC;
+    const int* idxC2;           // optional second row of tc, added (tor_bond_conv) or nullptr
+    int strideC;
+    const void* w1img;          // [hi|lo][8 k-chunks][8 row groups][8 rows][8] fp16 of W1aug * w1scale (bias in k = 60)
+    float inv_w1scale;
     const void* w2img;          // [W/100][hi|lo][8 k-chunks][14 row groups][8 rows][8] fp16 of W2aug * wscale
     float inv_wscale;
     const float* node_in;       // [n_in, D_IN]
@@ -232,8 +243,8 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
     float* osh = osc + Cfg::D_OUT;
     uint64_t* bars = reinterpret_cast<uint64_t*>(osc + 2 * 104);
     uint64_t *b_full = bars, *b_empty = bars + S::STAGES, *t_full = bars + 2 * S::STAGES, *t_empty = t_full + CF_SLOTS,
-             *a_ready = t_empty + CF_SLOTS;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
+             *a_ready = t_empty + CF_SLOTS;   // [0]: layer-1 operands in place, [1]: layer-2 operands; one phase per pair each
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // REDUX results live in uniform registers: everything derived from them (trip counts, the early exit, the MMA operands)
@@ -247,7 +258,8 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
     if (tid == 0) {
         for (int i = 0; i < S::STAGES; ++i) { tc_mbar_init(&b_full[i], 1); tc_mbar_init(&b_empty[i], 2); }
         for (int i = 0; i < CF_SLOTS; ++i) { tc_mbar_init(&t_full[i], 1); tc_mbar_init(&t_empty[i], 4); }
-        tc_mbar_init(a_ready, CF_WORKERS / 32);
+        tc_mbar_init(&a_ready[0], CF_WORKERS / 32);
+        tc_mbar_init(&a_ready[1], CF_WORKERS / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < Cfg::D_OUT; i += CF_THREADS) { osc[i] = a.oscale[i]; osh[i] = a.oshift[i]; }
@@ -263,13 +275,18 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
     if (warp == 10) {
         // ================= TMA producer (one thread): the weight chunks cycle through the ring, pair after pair =================
         if (lane == 0) {
-            const uint32_t total_chunks = (uint32_t)my_pairs * NCH;
+            const uint32_t total_chunks = (uint32_t)my_pairs * (NCH + 1);
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w2img);
             for (uint32_t g = 0; g < total_chunks; ++g) {
-                const uint32_t s = g % S::STAGES, u = g / S::STAGES;
+                const uint32_t s = g % S::STAGES, u = g / S::STAGES, c = g % (NCH + 1);   // c = 0: first-layer weights
                 tc_mbar_wait(&b_empty[s], (u & 1) ^ 1);
-                tc_mbar_expect_tx(&b_full[s], CF_B_STAGE);
-                tc_bulk_load(b_st + s * CF_B_STAGE, wsrc + (size_t)(g % NCH) * CF_B_STAGE, CF_B_STAGE, &b_full[s]);
+                if (c == 0) {
+                    tc_mbar_expect_tx(&b_full[s], CF_W1_BYTES);
+                    tc_bulk_load(b_st + s * CF_B_STAGE, a.w1img, CF_W1_BYTES, &b_full[s]);
+                } else {
+                    tc_mbar_expect_tx(&b_full[s], CF_B_STAGE);
+                    tc_bulk_load(b_st + s * CF_B_STAGE, wsrc + (size_t)(c - 1) * CF_B_STAGE, CF_B_STAGE, &b_full[s]);
+                }
             }
         }
     } else if (warp >= 8) {
@@ -285,6 +302,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
             const uint32_t b_base = tc_smem(b_st);
             const uint32_t a_hi_t = tmem_base + CF_A_COL + (uint32_t)(t * 32);
             const uint32_t a_lo_s = tc_smem(alo) + (uint32_t)(t * CF_ALO_TILE);
+            const uint32_t idesc1 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // first layer: N = 64
             uint32_t g = 0, use = 0;                                        // use: items issued by this warp so far
             for (int pi = 0; pi < my_pairs; ++pi) {
                 const int pair = (int)blockIdx.x + pi * (int)gridDim.x;
@@ -292,16 +310,45 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
                 const bool mine = t < ntile;
                 const bool probe_on = pi == 1 && lane == 0 && t == 0;
                 int pidx = 0;
-                // A operands of this pair are in place (vote-terminated waits: the warp provably stays converged)
-                cf_wait3(a_ready, (uint32_t)(pi & 1), a_ready, (uint32_t)(pi & 1), a_ready, (uint32_t)(pi & 1), lane);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                // barriers of one chunk: its weights landed, this tile's accumulator slot is drained
+                // barriers of one item: its weights landed, this tile's accumulator slot is drained
                 auto wait_chunk = [&](uint32_t gg, uint32_t uu) {
                     uint64_t* te = &t_empty[2 * (uu & 1) + t];
                     const uint32_t tp = ((uu >> 1) & 1) ^ 1;
                     cf_wait3(&b_full[gg % S::STAGES], (gg / S::STAGES) & 1, mine ? te : &b_full[gg % S::STAGES],
                              mine ? tp : (gg / S::STAGES) & 1, &b_full[gg % S::STAGES], (gg / S::STAGES) & 1, lane);
                 };
+                // ---- item 0 of the pair: hidden layer  D1[128, 64] = attr . W1aug  (vote-terminated waits keep the warp converged)
+                cf_wait3(&a_ready[0], (uint32_t)(pi & 1), &a_ready[0], (uint32_t)(pi & 1), &a_ready[0], (uint32_t)(pi & 1), lane);   // layer-1 A operands
+                wait_chunk(g, use);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                {
+                    const uint32_t s = g % S::STAGES;
+                    if (mine) {
+                        const uint32_t b_hi_s = b_base + s * CF_B_STAGE, b_lo_s = b_hi_s + CF_W1_BYTES / 2;
+                        const uint32_t slot = 2 * (use & 1) + (uint32_t)t;
+                        const uint32_t d = tmem_base + slot * CF_SLOT_COLS;
+#pragma unroll
+                        for (int combo = 0; combo < 3; ++combo) {
+                            const uint32_t bs = combo == 1 ? b_lo_s : b_hi_s;
+#pragma unroll
+                            for (int ks = 0; ks < TC_K / 16; ++ks) {
+                                const uint64_t bd = tc_smem_desc(bs + ks * 2 * 1024, 1024, 128);      // 8 row groups per K chunk
+                                if (combo < 2) cf_mma_f16_ts(d, a_hi_t + (uint32_t)(ks * 8), bd, idesc1, (combo | ks) ? 1u : 0u);
+                                else cf_mma_f16_ss(d, tc_smem_desc(a_lo_s + ks * 2 * 2048, 2048, 128), bd, idesc1, 1u);
+                            }
+                        }
+                        cf_commit(&t_full[slot]);
+                        cf_commit(&b_empty[s]);
+                        ++use;
+                    } else {
+                        if (lane == 0) tc_mbar_arrive(&b_empty[s]);
+                        __syncwarp();
+                    }
+                    ++g;
+                }
+                // ---- items 1 .. NCH: weight chunks
+                cf_wait3(&a_ready[1], (uint32_t)(pi & 1), &a_ready[1], (uint32_t)(pi & 1), &a_ready[1], (uint32_t)(pi & 1), lane);   // layer-2 A operands
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 CF_STAMP(0, 0, 0);
                 wait_chunk(g, use);
                 for (int c = 0; c < NCH; ++c, ++g) {
@@ -350,18 +397,21 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
         uint32_t item = 0;
         // indices of this thread's edge in pair `pr`: node range of the pair, first edge / edge count of its tile, gathered
         // node row, SH row
-        struct Idx { int n_lo, n_mid, n_hi, eb, ne, src, ce; };
+        struct Idx { int n_lo, n_mid, n_hi, eb, ne, src, ce, ib, ic, ic2; };
         auto fetch = [&](int pr) {
             Idx x;
             const int T0 = 2 * pr, nt = (T0 + 1 < n_tiles) ? 2 : 1;
             x.n_lo = a.tile_node[T0]; x.n_mid = a.tile_node[T0 + 1]; x.n_hi = a.tile_node[T0 + nt];
-            x.eb = 0; x.ne = 0; x.src = -1; x.ce = 0;
+            x.eb = 0; x.ne = 0; x.src = -1; x.ce = 0; x.ib = 0; x.ic = 0; x.ic2 = -1;
             if (tile < nt) {
                 x.eb = a.seg_ptr[tile ? x.n_mid : x.n_lo];
                 x.ne = a.seg_ptr[tile ? x.n_hi : x.n_mid] - x.eb;
                 if (row < x.ne) {
                     x.src = a.gather_idx ? a.gather_idx[x.eb + row] : x.eb + row;
                     x.ce = a.perm ? a.perm[x.eb + row] : x.eb + row;
+                    x.ib = a.idxB[x.eb + row];
+                    x.ic = a.idxC[x.eb + row];
+                    if (a.idxC2) x.ic2 = a.idxC2[x.eb + row];
                 }
             }
             return x;
@@ -377,32 +427,18 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
             const bool probe_on = pi == 1 && tid == 0;
             CF_STAMP(1, 50, 0);
             float shv[Cfg::SH_USED];
-            // ---- prologue 1: A operands -> TMEM (the MMAs of this pair can start as soon as they are there) ----
-            float rs = 0.f;
-            if (active) {
-                float h[64];
-                float m = 1.0f;
-                if (valid) {
-                    // edge-interleaved layout written by edge_hidden_kernel: [e / 32][16 quads][e % 32][4]
-                    const float4* hp = reinterpret_cast<const float4*>(a.himg) + (size_t)(e >> 5) * 512 + (e & 31);
+            // exactly-scaled FP16 split of one operand row (64 values): row * 2^s with max in [2^12, 2^13), hi -> TMEM, lo -> smem
+            // (K-major core matrices [k/8][m/8][m%8][k%8]; 8 consecutive rows write 128 contiguous bytes).  Returns 2^-s.
+            auto put_operand = [&](const float (&v)[64]) -> float {
+                float m = 1.0f;                                             // >= 1: column 60 holds the constant 1.0
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const float4 v = __ldg(hp + q * 32);
-                        h[4 * q] = v.x; h[4 * q + 1] = v.y; h[4 * q + 2] = v.z; h[4 * q + 3] = v.w;
-                        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 64; ++q) h[q] = 0.f;
-                }
-                // s = 2^(12 - floor(log2 m)): m * s in [2^12, 2^13); m >= 1 (the bias column holds 1.0)
+                for (int q = 0; q < 64; ++q) m = fmaxf(m, fabsf(v[q]));
                 const int ex = (int)((__float_as_uint(m) >> 23) & 0xFF) - 127;
                 const float sc = __uint_as_float((uint32_t)(127 + 12 - ex) << 23);
-                rs = __uint_as_float((uint32_t)(127 - 12 + ex) << 23) * a.inv_wscale;
                 uint32_t hi_p[32], lo_p[32];
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
-                    const float x0 = h[2 * c] * sc, x1 = h[2 * c + 1] * sc;
+                    const float x0 = v[2 * c] * sc, x1 = v[2 * c + 1] * sc;
                     const __half2 hh = __floats2half2_rn(x0, x1);           // packed conversions (F2FP), 2 values per instruction
                     const float2 hf = __half22float2(hh);
                     const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
@@ -410,17 +446,51 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
                     lo_p[c] = *reinterpret_cast<const uint32_t*>(&ll);
                 }
                 tc_tmem_st32(lane_base + CF_A_COL + (uint32_t)(tile * 32), hi_p);
-                // lo part: K-major core matrices [k/8][m/8][m%8][k%8]; 8 consecutive rows write 128 contiguous bytes
                 uint8_t* lo_dst = alo + tile * CF_ALO_TILE + (row >> 3) * 128 + (row & 7) * 16;
 #pragma unroll
                 for (int kc = 0; kc < 8; ++kc)
                     *reinterpret_cast<uint4*>(lo_dst + kc * 2048) = make_uint4(lo_p[4 * kc], lo_p[4 * kc + 1], lo_p[4 * kc + 2], lo_p[4 * kc + 3]);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> tensor-core (async proxy) reads
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                return __uint_as_float((uint32_t)(127 - 12 + ex) << 23);
+            };
+            // ---- prologue 1: edge attributes [emb | node B | node C] -> layer-1 A operand ----
+            float rs1 = 0.f;
+            if (active) {
+                float at[64];
+                if (valid) {
+                    const float4* pe = reinterpret_cast<const float4*>(a.emb + (size_t)ix.ce * 20);
+                    const float2* pb = reinterpret_cast<const float2*>(a.tb + (size_t)ix.ib * a.strideB);
+                    const float2* pc = reinterpret_cast<const float2*>(a.tc + (size_t)ix.ic * a.strideC);
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) {
+                        const float4 v = __ldg(pe + q);
+                        at[4 * q] = v.x; at[4 * q + 1] = v.y; at[4 * q + 2] = v.z; at[4 * q + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 10; ++q) {
+                        const float2 vb = __ldg(pb + q), vc = __ldg(pc + q);
+                        at[20 + 2 * q] = vb.x; at[21 + 2 * q] = vb.y;
+                        at[40 + 2 * q] = vc.x; at[41 + 2 * q] = vc.y;
+                    }
+                    if (ix.ic2 >= 0) {
+                        const float2* pc2 = reinterpret_cast<const float2*>(a.tc + (size_t)ix.ic2 * a.strideC);
+#pragma unroll
+                        for (int q = 0; q < 10; ++q) {
+                            const float2 vc = __ldg(pc2 + q);
+                            at[40 + 2 * q] += vc.x; at[41 + 2 * q] += vc.y;
+                        }
+                    }
+                    at[60] = 1.0f; at[61] = 0.f; at[62] = 0.f; at[63] = 0.f;   // k = 60 multiplies the bias row of W1aug
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 64; ++q) at[q] = 0.f;
+                }
+                rs1 = put_operand(at) * a.inv_w1scale;
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) tc_mbar_arrive(a_ready);
+            if (lane == 0) tc_mbar_arrive(&a_ready[0]);                    // layer-1 operands in place
             CF_STAMP(1, 50, 1);
             // ---- prologue 2 (under the first MMAs): gathered node rows -> smem (warp-cooperative, coalesced), SH -> registers,
             //      seg_ptr of the pair's nodes -> smem for the epilogue ----
@@ -450,14 +520,41 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
                         }
                     }
                 }
-                // the power-of-two operand scales are undone exactly by scaling the spherical harmonics (Z is linear in them)
 #pragma unroll
-                for (int i = 0; i < Cfg::SH_USED; ++i) shv[i] = valid ? __ldg(a.sh + (size_t)ix.ce * a.sh_stride + i) * rs : 0.f;
+                for (int i = 0; i < Cfg::SH_USED; ++i) shv[i] = valid ? __ldg(a.sh + (size_t)ix.ce * a.sh_stride + i) : 0.f;
             } else {
 #pragma unroll
                 for (int i = 0; i < Cfg::SH_USED; ++i) shv[i] = 0.f;
             }
             __syncwarp();
+            // ---- prologue 3: hidden activations h = ReLU(D1) from tensor memory -> layer-2 A operand ----
+            float rs = 0.f;
+            if (active) {
+                const uint32_t slot = 2 * (item & 1) + (uint32_t)tile, use = item >> 1;
+                if (lane == 0) tc_mbar_wait(&t_full[slot], use & 1);
+                __syncwarp();
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                float h[64];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) cf_tmem_ld16(lane_base + slot * CF_SLOT_COLS + 16 * q, h + 16 * q);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int q = 0; q < 4; ++q) cf_wait_ld16(h + 16 * q);      // (register dependency only)
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) tc_mbar_arrive(&t_empty[slot]);
+                ++item;
+#pragma unroll
+                for (int q = 0; q < 60; ++q) h[q] = fmaxf(h[q] * rs1, 0.f);
+                h[60] = valid ? 1.0f : 0.f; h[61] = 0.f; h[62] = 0.f; h[63] = 0.f;   // k = 60 multiplies the bias row of W2aug
+                rs = put_operand(h) * a.inv_wscale;
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(&a_ready[1]);                    // layer-2 operands in place
+            // the power-of-two operand scales are undone exactly by scaling the spherical harmonics (Z is linear in them)
+#pragma unroll
+            for (int i = 0; i < Cfg::SH_USED; ++i) shv[i] *= rs;
             // indices of the next pair: their round trips hide behind the main loop
             Idx nx = ix;
             if (pi + 1 < my_pairs) nx = fetch(pair + (int)gridDim.x);

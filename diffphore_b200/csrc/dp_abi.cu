@@ -136,25 +136,6 @@ int dp_edge_mlp_tc(const float* emb, const int32_t* perm, const float* tb, const
     return edge_mlp_tc_launch(t, ST(stream));
 }
 
-int dp_edge_hidden(const float* emb, const int32_t* perm, const float* tb, const int32_t* idxB, int32_t strideB,
-                   const float* tc, const int32_t* idxC, const int32_t* idxC2, int32_t strideC, const float* w1,
-                   const float* b1, const int32_t* n_edges_dev, int32_t n_edges_cap, float* h_out, void* stream) {
-    NEED(tc != nullptr && h_out != nullptr, "dp_edge_hidden: null argument");
-    if (n_edges_cap <= 0) return DP_OK;
-    EdgeMlpArgs a;
-    a.emb = emb; a.perm = perm; a.tb = tb; a.idxB = idxB; a.strideB = strideB; a.tc = tc; a.idxC = idxC; a.idxC2 = idxC2;
-    a.strideC = strideC; a.w1 = w1; a.b1 = b1; a.w2t = nullptr; a.in_dim = 60; a.hid = 60; a.W = 0;
-    a.n_edges_dev = n_edges_dev; a.n_edges = n_edges_cap; a.out = nullptr;
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    }
-    edge_hidden_kernel<<<min((n_edges_cap + EH_TILE - 1) / EH_TILE, n_sm * 6), EH_THREADS, 0, ST(stream)>>>(a, h_out, 1);
-    return dp_check_launch("dp_edge_hidden");
-}
-
 int dp_build_tiles(const int32_t* seg_ptr, const int32_t* node_ptr, int32_t n_graphs, int32_t* cnt, int32_t* start,
                    int32_t* tile_node, int32_t* n_tiles_out, void* stream) {
     if (n_graphs <= 0) return DP_OK;
@@ -168,15 +149,20 @@ static long long* g_cf_dbg_host = nullptr;
 /* profiling aid (not part of the public header): per-phase clock stamps of dp_conv_fused (layer 3) */
 int dp_debug_set_cf_probe(long long* buf) { g_cf_dbg_host = buf; return DP_OK; }
 
-int dp_conv_fused(int32_t layer, const float* h, const void* w2img, float inv_wscale, const float* node_in,
-                  const int32_t* gather_idx, const int32_t* perm, const float* sh, int32_t sh_stride,
-                  const int32_t* seg_ptr, const int32_t* tile_node, const int32_t* n_tiles_dev, int32_t n_tiles_cap,
-                  const float* oscale, const float* oshift, float* out, const float* residual, int32_t res_dim,
-                  int32_t mode, void* stream) {
+int dp_conv_fused(int32_t layer, const float* emb, const int32_t* perm, const float* tb, const int32_t* idxB, int32_t strideB,
+                  const float* tc, const int32_t* idxC, const int32_t* idxC2, int32_t strideC, const void* w1img,
+                  float inv_w1scale, const void* w2img, float inv_wscale, const float* node_in, const int32_t* gather_idx,
+                  const float* sh, int32_t sh_stride, const int32_t* seg_ptr, const int32_t* tile_node,
+                  const int32_t* n_tiles_dev, int32_t n_tiles_cap, const float* oscale, const float* oshift, float* out,
+                  const float* residual, int32_t res_dim, int32_t mode, void* stream) {
     NEED(mode != 1 || residual != nullptr, "dp_conv_fused: mode 1 needs a residual");
-    NEED(h && w2img && node_in && sh && seg_ptr && tile_node && out, "dp_conv_fused: null argument");
+    NEED(emb && tb && idxB && tc && idxC && w1img && w2img && node_in && sh && seg_ptr && tile_node && out,
+         "dp_conv_fused: null argument");
+    NEED(strideB % 2 == 0 && strideC % 2 == 0, "dp_conv_fused: node rows must be 8-byte aligned");
     ConvFusedArgs a;
-    a.himg = h; a.w2img = w2img; a.inv_wscale = inv_wscale; a.node_in = node_in; a.gather_idx = gather_idx; a.perm = perm;
+    a.emb = emb; a.tb = tb; a.idxB = idxB; a.strideB = strideB; a.tc = tc; a.idxC = idxC; a.idxC2 = idxC2; a.strideC = strideC;
+    a.w1img = w1img; a.inv_w1scale = inv_w1scale;
+    a.w2img = w2img; a.inv_wscale = inv_wscale; a.node_in = node_in; a.gather_idx = gather_idx; a.perm = perm;
     a.sh = sh; a.sh_stride = sh_stride; a.seg_ptr = seg_ptr; a.tile_node = tile_node; a.n_tiles_dev = n_tiles_dev;
     a.n_tiles = n_tiles_cap; a.oscale = oscale; a.oshift = oshift; a.out = out; a.residual = residual; a.res_dim = res_dim;
     a.mode = mode;

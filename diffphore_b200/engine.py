@@ -62,6 +62,8 @@ class ConvWeights:
                 img, s112 = _make_w2img112(_f32(w3).cpu(), _f32(sd[prefix + '.fc.3.bias']).cpu())
                 assert s112 == self.inv_wscale
                 self.w2img112 = img.to(device)
+                img, self.inv_w1scale = _make_w1img(_f32(sd[prefix + '.fc.0.weight']).cpu(), _f32(sd[prefix + '.fc.0.bias']).cpu())
+                self.w1img = img.to(device)
         # eval BatchNorm (e3nn.nn.BatchNorm) and path weights folded into per-component scale/shift
         bw, bb = sd[prefix + '.batch_norm.weight'].double(), sd[prefix + '.batch_norm.bias'].double()
         rm, rv = sd[prefix + '.batch_norm.running_mean'].double(), sd[prefix + '.batch_norm.running_var'].double()
@@ -123,6 +125,23 @@ def _make_w2img112(w3, b3):
     hi = xs.half()
     lo = (xs - hi.float()).half()
     img = torch.stack([hi, lo], 1).reshape(nch, 2, 14, 8, 8, 8).permute(0, 1, 4, 2, 3, 5)     # [c][h][kc][ng][r][j]
+    return img.contiguous().reshape(-1).view(torch.uint8), 2.0 ** (-k)
+
+
+def _make_w1img(w1, b1):
+    """Shared-memory image of the first-layer weights for dp_conv_fused: W1aug[n, 0:60] = fc.0.weight, [n, 60] = fc.0.bias,
+    W1aug[60, 60] = 1 (passes the constant-1 attribute column through ReLU into the bias column of the second layer), zero
+    padded to 64 x 64, scaled by 2^k into [2^12, 2^13), fp16 hi | lo, [hi|lo][k/8][n/8][n%8][k%8].  Returns (image, 2^-k)."""
+    x = torch.zeros(64, 64, dtype=torch.float32)
+    x[:60, :60] = w1
+    x[:60, 60] = b1
+    x[60, 60] = 1.0
+    m = float(x.abs().max())
+    k = 12 - math.floor(math.log2(m)) if m > 0 and math.isfinite(m) else 0
+    xs = x * (2.0 ** k)
+    hi = xs.half()
+    lo = (xs - hi.float()).half()
+    img = torch.stack([hi, lo], 0).reshape(2, 8, 8, 8, 8).permute(0, 3, 1, 2, 4)                 # [h][kc][ng][r][j]
     return img.contiguous().reshape(-1).view(torch.uint8), 2.0 ** (-k)
 
 
@@ -401,7 +420,8 @@ class PackedBatch:
         ps = torch.zeros(self.n_ph, 20, device=device)
         for i in range(3):
             ps = ps + w.ph_tables[i][px[:, i].long()]
-        ps = ps + px[:, 3:5] @ w.ph_lin_w[:, 0:2].T
+        # explicit products in a fixed order (a cuBLAS matmul may pick a size-dependent kernel => batch-composition-dependent rounding)
+        ps = ps + px[:, 3:4] * w.ph_lin_w[:, 0][None, :] + px[:, 4:5] * w.ph_lin_w[:, 1][None, :]
         self.lig_static, self.ph_static = ls.contiguous(), ps.contiguous()
         # capacities of the dynamic edge sets
         k = weights.cfg['max_neighbors']
@@ -412,7 +432,7 @@ class PackedBatch:
 class Workspace:
     """All per-step device buffers for one PackedBatch."""
 
-    def __init__(self, b, weights, wbuf=None):
+    def __init__(self, b, weights, wbuf=None, fused=True):
         dev = b.device
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         i = lambda *s: torch.empty(*s, dtype=torch.int32, device=dev)
@@ -429,9 +449,18 @@ class Workspace:
         self.t_emb, self.t_sh, self.t_n = f(max(b.tor_cap, 1), 20), f(max(b.tor_cap, 1), 8), i(1)
         self.tor_feat = f(max(b.n_rot, 1), 40)
         self.tr, self.rot, self.tor = f(b.B, 3), f(b.B, 3), f(max(b.n_rot, 1))
-        w_elems = max(b.ll_cap * 2200, b.n_cross * 2200, b.n_pp * 1600, b.tor_cap * 1600, b.n_lig * 200, 1)
+        # HBM scratch of the unfused kernels (dp_edge_mlp(_tc) -> dp_tp_scatter): always needed by final_conv (hid = 40), by
+        # every edge set when DIFFPHORE_CONV=split, and by static edge sets with a node of more than 128 edges
+        split = [(b.n_lig, 200)]
+        if not fused:
+            split += [(b.ll_cap, 2200), (b.tor_cap, 1600)]
+        if not fused or b.tiles_cross_lig is None or b.tiles_cross_ph is None:
+            split.append((b.n_cross, 2200))
+        if not fused or b.tiles_pp is None:
+            split.append((b.n_pp, 1600))
+        w_elems = max(max(e * w for e, w in split), 1)
         self.w_elems = w_elems
-        max_edges = max(b.ll_cap, b.n_cross, b.n_pp, b.tor_cap, 1)
+        max_edges = max(max(e for e, w in split if w != 200) if len(split) > 1 else 0, 1)
         self.hbuf = f(((max_edges + 127) // 128) * 128 * 64)          # hidden activations of dp_edge_mlp_tc (pass 1 -> pass 2)
         self.wbuf = wbuf if wbuf is not None and wbuf.numel() >= w_elems else f(w_elems)   # per-edge TP weights
         # node-aligned tiles of the dynamic edge sets (dp_build_tiles): <= 2 E / 128 + 1 tiles per graph
@@ -452,7 +481,7 @@ class Engine:
         # second MLP layer on tcgen05 tensor cores (3xTF32) or on CUDA cores (FFMA); env DIFFPHORE_EDGE_MLP=ffma|tc
         import os
         self.use_tc = os.environ.get('DIFFPHORE_EDGE_MLP', 'tc') == 'tc'
-        # DIFFPHORE_CONV=fused (default): dp_edge_hidden + dp_conv_fused, the per-edge weights never leave the SM;
+        # DIFFPHORE_CONV=fused (default): dp_conv_fused, the per-edge hidden activations and weights never leave the SM;
         # DIFFPHORE_CONV=split: dp_edge_mlp(_tc) -> HBM -> dp_tp_scatter (kept for A/B measurements and as the path for
         # edge sets the fused kernel does not cover: hid != 60, W % 100 != 0, nodes with more than 128 edges)
         self.use_fused = os.environ.get('DIFFPHORE_CONV', 'fused') == 'fused'
@@ -461,7 +490,7 @@ class Engine:
         """Upload a batch and run the static-geometry setup kernels.  wbuf: optional shared per-edge weight buffer
         (chunks run one after the other on one stream, so they can share it)."""
         b = PackedBatch(graphs, samples_per_graph, self.w, self.w.device)
-        ws = Workspace(b, self.w, wbuf)
+        ws = Workspace(b, self.w, wbuf, self.use_fused)
         st = torch.cuda.current_stream().cuda_stream
         sw = self.w.sw
         L.check(self.lib.dp_pp_setup(L.ptr(b.ppos), L.ptr(b.pp_src), L.ptr(b.pp_dst), b.n_pp, sw, L.ptr(ws.pp_h),
@@ -483,18 +512,14 @@ class Engine:
             e0 = tm.start()
         if self.use_fused and tiles is not None and cw.w2img112 is not None:
             tile_node, n_tiles_dev, n_tiles_cap = tiles
-            L.check(self.lib.dp_edge_hidden(p(emb), p(perm), p(tb), p(idxB), tb.shape[1], p(tc), p(idxC), p(idxC2), tc.shape[1],
-                                            p(cw.w1), p(cw.b1), p(n_dev), n_cap, p(ws.hbuf), st), 'dp_edge_hidden')
+            L.check(self.lib.dp_conv_fused(cw.layer_id, p(emb), p(perm), p(tb), p(idxB), tb.shape[1], p(tc), p(idxC), p(idxC2),
+                                           tc.shape[1], p(cw.w1img), cw.inv_w1scale, p(cw.w2img112), cw.inv_wscale, p(node_in),
+                                           p(gather), p(sh), sh_stride, p(seg), p(tile_node), p(n_tiles_dev), n_tiles_cap,
+                                           p(cw.oscale), p(cw.oshift), p(out), p(residual), res_dim, mode, st), 'dp_conv_fused')
             if tm is not None:
-                tm.stop('edge_hidden', name, e0, n_rec, dict(in_dim=cw.in_dim, hid=cw.hid, W=0))
-                e0 = tm.start()
-            L.check(self.lib.dp_conv_fused(cw.layer_id, p(ws.hbuf), p(cw.w2img112), cw.inv_wscale, p(node_in), p(gather), p(perm),
-                                           p(sh), sh_stride, p(seg), p(tile_node), p(n_tiles_dev), n_tiles_cap, p(cw.oscale),
-                                           p(cw.oshift), p(out), p(residual), res_dim, mode, st), 'dp_conv_fused')
-            if tm is not None:
-                tm.stop('conv_fused', name, e0, n_rec, dict(W=cw.W, hid=cw.hid, d_in=cw.d_in, d_out=cw.d_out, n_out=n_out,
-                                                            tp_flops=cw.tp_flops))
-            ws.n_launches += 2
+                tm.stop('conv_fused', name, e0, n_rec, dict(W=cw.W, hid=cw.hid, in_dim=cw.in_dim, d_in=cw.d_in, d_out=cw.d_out,
+                                                            n_out=n_out, tp_flops=cw.tp_flops))
+            ws.n_launches += 1
             return
         if self.use_tc and cw.w2img is not None:
             L.check(self.lib.dp_edge_mlp_tc(p(emb), p(perm), p(tb), p(idxB), tb.shape[1], p(tc), p(idxC), p(idxC2), tc.shape[1],

@@ -2,7 +2,7 @@
 
 Algorithmic bytes of one dp_tp_scatter launch:  E*(4W + 4 D_in + 4 D_sh + 8) + N_out*4*D_out
 Algorithmic flops of one dp_edge_mlp launch:                 2*E*(in*hid + (hid+1)*W)
-Algorithmic flops of one dp_conv_fused launch:               E*(2*(hid+1)*W + tp_flops)   (second MLP layer + channel mixing;
+Algorithmic flops of one dp_conv_fused launch:               E*(2*(in+1)*hid + 2*(hid+1)*W + tp_flops)   (MLP + channel mixing;
     the tensor pipe executes 3 * 112/100 times the first term: 2-way FP16 split, chunks padded 100 -> 112 columns)
 """
 import torch
@@ -37,8 +37,8 @@ class KernelTimer:
             if kind == 'tp_scatter':
                 a['bytes'] += E * (4 * m['W'] + 4 * m['d_in'] + 4 * m['d_sh'] + 8) + m['n_out'] * 4 * m['d_out']
             elif kind == 'conv_fused':
-                a['flops'] += float(E) * (2.0 * (m['hid'] + 1) * m['W'] + m['tp_flops'])
-                a['bytes'] += float(E) * (256 + 4 * m['d_in'] + 44) + m['n_out'] * 4 * m['d_out']
+                a['flops'] += float(E) * (2.0 * (m['in_dim'] + 1) * m['hid'] + 2.0 * (m['hid'] + 1) * m['W'] + m['tp_flops'])
+                a['bytes'] += float(E) * (240 + 4 * m['d_in'] + 44) + m['n_out'] * 4 * m['d_out']
             elif kind == 'edge_hidden':
                 a['flops'] += 2.0 * E * m['in_dim'] * m['hid']
                 a['bytes'] += float(E) * (256 + 240)
@@ -59,8 +59,8 @@ class KernelTimer:
         n = 0
         for kind, name, sec, E, m in self._resolved():
             if kind == 'conv_fused':
-                tot_f += float(E) * (2.0 * (m['hid'] + 1) * m['W'] + m['tp_flops'])
-                tot_mma += float(E) * 2.0 * 64 * m['W'] * 1.12 * 3
+                tot_f += float(E) * (2.0 * (m['in_dim'] + 1) * m['hid'] + 2.0 * (m['hid'] + 1) * m['W'] + m['tp_flops'])
+                tot_mma += float(E) * 2.0 * 64 * (m['W'] * 1.12 + 64) * 3
                 tot_b += float(E) * (4 * m['W'] + 4 * m['d_in'] + 4 * 9 + 8) + m['n_out'] * 4 * m['d_out']
                 tot_s += sec
                 n += 1
@@ -72,7 +72,7 @@ class KernelTimer:
                     launches=n, flops_per_launch=tot_f / n, ms_per_launch=1e3 * tot_s / n,
                     issued_mma_tflops=tot_mma / tot_s / 1e12, issued_mma_frac=tot_mma / tot_s / 1e12 / peak_tflops,
                     equiv_hbm_gbs=tot_b / tot_s / 1e9, equiv_hbm_frac=tot_b / tot_s / 1e9 / hbm_gbs,
-                    note='algorithmic FLOPs = 2*E*61*W (second MLP layer) + E*tp_flops; the fp32-parity FP16 split issues 3 '
+                    note='algorithmic FLOPs = E*(2*61*60 + 2*61*W + tp_flops) (both MLP layers + channel mixing); the fp32-parity FP16 split issues 3 '
                          'MMAs per product and pads 100-column chunks to N=112 (issued_mma_*); equiv_hbm_* = bytes the '
                          'unfused dp_tp_scatter would stream (SURVEY 8d) / this kernel\'s time')
 

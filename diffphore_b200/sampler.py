@@ -30,13 +30,14 @@ def random_rotations(n, generator=None, device='cpu'):
 
 class DenoisingSampler:
     def __init__(self, weights: ModelWeights, inference_steps=20, so3_norm=None, torus_norm=None,
-                 weight_buffer_bytes=24 << 30, no_final_step_noise=False):
+                 weight_buffer_bytes=24 << 30, no_final_step_noise=False, resident_bytes=48 << 30):
         self.w = weights
         self.engine = Engine(weights)
         self.steps = inference_steps
         self.so3 = so3_norm or So3ScoreNorm()
         self.torus = torus_norm or TorusScoreNorm()
         self.weight_buffer_bytes = weight_buffer_bytes
+        self.resident_bytes = resident_bytes
         self.no_final_step_noise = no_final_step_noise
         sched = get_t_schedule(inference_steps)
         rows = []
@@ -50,7 +51,20 @@ class DenoisingSampler:
 
     # ------------------------------------------------------------------
     def graphs_per_chunk(self, graphs, samples):
+        """Pairs per resident chunk.  Unfused kernels: the worst-case per-edge weight scratch must fit `weight_buffer_bytes`.
+        Fused kernels keep the weights on chip, so only node / edge features count (~0.2 MB per cfg2 graph): cap the chunk
+        at `max_graphs_per_chunk` graphs (pair x sample) to bound the resident working set."""
         k = self.w.cfg['max_neighbors']
+        if self.engine.use_fused:
+            worst = 1
+            for g in graphs:
+                n, P = g['ligand'].pos.shape[0], g['phore'].pos.shape[0]
+                eb = g['ligand', 'ligand'].edge_index.shape[1]
+                e_all = eb + n * min(n - 1, k + 1) + 2 * n * P + g['phore', 'phore'].edge_index.shape[1]
+                worst = max(worst, e_all * 4 * 60 + (n + P) * 4 * 600)      # edge embeddings / SH / indices + node features
+                if n > 128 or P > 128:                                      # a cross node with > 128 edges: unfused scratch too
+                    worst = max(worst, n * P * 2200 * 4)
+            return max(1, int(self.resident_bytes // (worst * samples)))
         worst = 1
         for g in graphs:
             n, P = g['ligand'].pos.shape[0], g['phore'].pos.shape[0]

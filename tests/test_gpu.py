@@ -141,7 +141,7 @@ def test_full_size_properties_cfg2():
     assert torch.isfinite(pos).all()
     pos = pos.reshape(P, S, 32, 3)
     assert torch.equal(pos, pos[:, :1].expand_as(pos))                         # (i)
-    small = DenoisingSampler(ModelWeights(sd, dev), steps, weight_buffer_bytes=64 << 20)
+    small = DenoisingSampler(ModelWeights(sd, dev), steps, weight_buffer_bytes=64 << 20, resident_bytes=4 << 20)
     pos1, _ = small.run(graphs[:17], 1, noise=[dict(tr=z['tr'][:17], rot=z['rot'][:17], tor=z['tor'][:offs[17]]) for z in noise1],
                         init=dict(tor=init1['tor'][:offs[17]], rot=init1['rot'][:17], tr=init1['tr'][:17]))
     assert len(small.prepare(graphs[:17], 1)) > 1                              # really chunked

@@ -1,10 +1,10 @@
-"""GPU-box aid: dp_edge_hidden + dp_conv_fused against dp_edge_mlp_tc + dp_tp_scatter on one synthetic convolution
+"""GPU-box aid: dp_conv_fused against dp_edge_mlp_tc + dp_tp_scatter on one synthetic convolution
 (same inputs, same weights), with CUDA-event timings of both pipelines."""
 import math, os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'src'))
 from diffphore_b200 import lib as L
-from diffphore_b200.engine import _make_w2img, _make_w2img112, greedy_tiles
+from diffphore_b200.engine import _make_w2img, _make_w2img112, _make_w1img, greedy_tiles
 import numpy as np
 lib = L.load(); p = L.ptr
 dev = torch.device('cuda:0')
@@ -25,7 +25,9 @@ def run(layer, n_nodes, deg, seed=0, mode=0, reps=3):
     ic = torch.randint(0, n_in, (E,), generator=g, dtype=torch.int32).to(dev)
     gat = torch.randint(0, n_in, (E,), generator=g, dtype=torch.int32).to(dev)
     sh = torch.randn(E, shs, generator=g).to(dev)
-    w1, b1 = (torch.randn(60, 60, generator=g) / 8).to(dev), torch.randn(60, generator=g).to(dev)
+    w1c, b1c = torch.randn(60, 60, generator=g) / 8, torch.randn(60, generator=g)
+    w1, b1 = w1c.to(dev), b1c.to(dev)
+    img1, inv1 = _make_w1img(w1c, b1c); img1 = img1.to(dev)
     w3, b3 = torch.randn(W, 60, generator=g) / 8, torch.randn(W, generator=g)
     img, inv_ws = _make_w2img(w3, b3); img = img.to(dev)
     img112, inv2 = _make_w2img112(w3, b3); img112 = img112.to(dev)
@@ -48,16 +50,20 @@ def run(layer, n_nodes, deg, seed=0, mode=0, reps=3):
                                   p(res), d_in, mode, n_nodes, st), 'tp')
 
     def fused(out):
-        L.check(lib.dp_edge_hidden(p(emb), None, p(nodes20), p(ib), 100, p(nodes20), p(ic), None, 100, p(w1), p(b1), None, E,
-                                   p(hbuf), st), 'hidden')
-        L.check(lib.dp_conv_fused(layer, p(hbuf), p(img112), inv_ws, p(nodes), p(gat), None, p(sh), shs, p(segd), p(tile_node),
-                                  None, n_tiles, p(oscale), p(oshift), p(out), p(res), d_in, mode, st), 'fused')
+        L.check(lib.dp_conv_fused(layer, p(emb), None, p(nodes20), p(ib), 100, p(nodes20), p(ic), None, 100, p(img1), inv1, p(img112),
+                                  inv_ws, p(nodes), p(gat), p(sh), shs, p(segd), p(tile_node), None, n_tiles, p(oscale), p(oshift),
+                                  p(out), p(res), d_in, mode, st), 'fused')
 
     oa, ob = out0.clone(), out0.clone()
     split(oa); fused(ob)
     torch.cuda.synchronize()
     err = float((oa - ob).norm() / oa.norm())
     mx = float((oa - ob).abs().max())
+    if err > 1e-5:
+        bad = ((oa - ob).abs().max(1).values > 1e-3 * oa.abs().max()).nonzero().flatten().cpu().numpy()
+        tl = np.asarray(tiles + [n_nodes])
+        print('   BAD nodes', len(bad), 'of', n_nodes, 'first', bad[:12], 'deg', degs[bad[:12]], 'tile', np.searchsorted(tl, bad[:12], 'right') - 1,
+              'seg', seg[bad[:12]], 'n_tiles', n_tiles)
     tm = {}
     for name, fn in (('split', split), ('fused', fused)):
         o = out0.clone()
