@@ -32,7 +32,6 @@
 #define CF_N 112                                      // MMA N (chunk padded to a multiple of 16)
 #define CF_B_HALF (CF_N * TC_K * 2)                   // one fp16 operand image (hi or lo) of a chunk: 14336 B
 #define CF_B_STAGE (2 * CF_B_HALF)                    // hi | lo
-#define CF_XB 32                                      // node rows per gather batch of a warp
 #define CF_SLOTS 4                                    // accumulator slots (TMEM), rotating over the (chunk, tile) items
 #define CF_SLOT_COLS 112
 #define CF_A_COL 448                                  // A hi operands: tile t -> TMEM columns 448 + 32 t
@@ -165,16 +164,51 @@ __device__ __forceinline__ void cf_wait3(uint64_t* b0, uint32_t p0, uint64_t* b1
 }
 __device__ __forceinline__ void cf_bar_workers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// Accumulator layout: the per-edge output row is kept as float2 pairs of ADJACENT OUTPUT CHANNELS (v, v + 1) of one component k,
+// acc2[off/2 + k * V/2 + v/2], so that one FFMA2 (sm_100 packed fp32 FMA, __ffma2_rn: two IEEE fmas) consumes two adjacent
+// weight columns.  cf_acc_slot maps an e3nn output index d = off + v * K + k to 2 * pair + half.
+template <class Cfg>
+__host__ __device__ constexpr int cf_acc_slot(int d) {
+    for (int oi = 0; oi < Cfg::NO; ++oi) {
+        const TpOut t = Cfg::outs[oi];
+        const int K = 2 * t.lo + 1;
+        if (d >= t.off && d < t.off + t.V * K) {
+            const int r = d - t.off, v = r / K, k = r % K;
+            return 2 * (t.off / 2 + k * (t.V / 2) + v / 2) + (v & 1);
+        }
+    }
+    return 0;
+}
+
+template <class Cfg, int D>
+__device__ __forceinline__ float cf_acc_get(const float2 (&acc)[Cfg::D_OUT / 2]) {
+    if constexpr (D < Cfg::D_OUT) {
+        constexpr int sl = cf_acc_slot<Cfg>(D);                            // compile-time evaluation
+        return (sl & 1) ? acc[sl >> 1].y : acc[sl >> 1].x;
+    } else {
+        return 0.f;
+    }
+}
+// stage this thread's output row (e3nn order) as float4 quads
+template <class Cfg, int Q, int NQ>
+__device__ __forceinline__ void cf_stage_row(const float2 (&acc)[Cfg::D_OUT / 2], float* dst) {
+    if constexpr (Q < NQ) {
+        *reinterpret_cast<float4*>(dst + 4 * Q) = make_float4(cf_acc_get<Cfg, 4 * Q>(acc), cf_acc_get<Cfg, 4 * Q + 1>(acc),
+                                                              cf_acc_get<Cfg, 4 * Q + 2>(acc), cf_acc_get<Cfg, 4 * Q + 3>(acc));
+        cf_stage_row<Cfg, Q + 1, NQ>(acc, dst);
+    }
+}
+
 // One 100-column chunk of path P (rows u0 .. u0 + 100/V - 1), this thread's edge.
 template <class Cfg, int P>
 __device__ __forceinline__ void cf_chunk(uint32_t tslot, const float* __restrict__ xrow, int u0, const float* shv,
-                                         float (&acc)[Cfg::D_OUT]) {
+                                         float2 (&acc)[Cfg::D_OUT / 2]) {
     constexpr TpPath p = Cfg::paths[P];
     constexpr TpOut o = Cfg::outs[p.oi];
     constexpr int V = o.V, K = 2 * o.lo + 1, D1 = 2 * p.l1 + 1;
-    static_assert(CF_CHUNK % V == 0, "chunk must hold whole weight rows");
+    static_assert(CF_CHUNK % V == 0 && V % 2 == 0 && o.off % 2 == 0, "chunk must hold whole weight rows of channel pairs");
     float wv[2][16];
-    float z[3] = {0.f, 0.f, 0.f};
+    float2 zz[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
     cf_tmem_ld16(tslot, wv[0]);
 #pragma unroll
     for (int q = 0; q < 7; ++q) {
@@ -182,17 +216,22 @@ __device__ __forceinline__ void cf_chunk(uint32_t tslot, const float* __restrict
         if (q + 1 < 6) cf_tmem_ld16(tslot + 16 * (q + 1), wv[(q + 1) & 1]);
         else if (q + 1 == 6) cf_tmem_ld4(tslot + 96, wv[0]);
 #pragma unroll
-        for (int j = 0; j < (q < 6 ? 16 : 4); ++j) {
+        for (int j = 0; j < (q < 6 ? 16 : 4); j += 2) {
             const int col = 16 * q + j, r = col / V, v = col % V;
             if (v == 0) {                                                  // next weight row: Z[u, :] = CG(x[u, :], sh)
-                float xv[3];
+                float xv[3], z[3] = {0.f, 0.f, 0.f};
 #pragma unroll
                 for (int i = 0; i < D1; ++i) xv[i] = xrow[p.in_off + (u0 + r) * D1 + i];
                 dp_cg<p.l1, p.l2, o.lo>(xv, shv + p.sh_off, z);
-            }
-            const float wj = wv[q & 1][j];
 #pragma unroll
-            for (int k = 0; k < K; ++k) acc[o.off + v * K + k] = fmaf(wj, z[k], acc[o.off + v * K + k]);
+                for (int k = 0; k < K; ++k) zz[k] = make_float2(z[k], z[k]);
+            }
+            const float2 w2 = make_float2(wv[q & 1][j], wv[q & 1][j + 1]);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                float2& a2 = acc[o.off / 2 + k * (V / 2) + v / 2];
+                a2 = __ffma2_rn(w2, zz[k], a2);
+            }
         }
     }
 }
@@ -200,7 +239,7 @@ __device__ __forceinline__ void cf_chunk(uint32_t tslot, const float* __restrict
 template <class Cfg, int P, bool PROBE>
 __device__ __forceinline__ void cf_paths(uint32_t tmem_lane_base, uint64_t* t_full, uint64_t* t_empty, uint32_t& item, int tile,
                                          int ntile, bool active, const float* __restrict__ xrow, const float* shv,
-                                         float (&acc)[Cfg::D_OUT], int lane, bool probe_on, uint32_t item0, long long* a_dbg) {
+                                         float2 (&acc)[Cfg::D_OUT / 2], int lane, bool probe_on, uint32_t item0, long long* a_dbg) {
     if constexpr (P < Cfg::NP) {
         constexpr TpPath p = Cfg::paths[P];
         constexpr int V = Cfg::outs[p.oi].V;
@@ -349,14 +388,16 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
                 // ---- items 1 .. NCH: weight chunks
                 cf_wait3(&a_ready[1], (uint32_t)(pi & 1), &a_ready[1], (uint32_t)(pi & 1), &a_ready[1], (uint32_t)(pi & 1), lane);   // layer-2 A operands
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                CF_STAMP(0, 0, 0);
-                wait_chunk(g, use);
                 for (int c = 0; c < NCH; ++c, ++g) {
                     const uint32_t s = g % S::STAGES;
+                    // Wait at the top of the item (weights landed, slot drained).  A wait inside the item (before its last
+                    // MMAs) measured slower: with a 3-stage weight ring the NEXT chunk's weights are still in flight then,
+                    // and the item's own tail MMAs would be held back behind that round trip.
+                    CF_STAMP(0, pidx, 0);
+                    wait_chunk(g, use);
                     if (!mine) {                                            // single-tile pair: only release the weight stage
                         if (lane == 0) tc_mbar_arrive(&b_empty[s]);
                         __syncwarp();
-                        if (c + 1 < NCH) wait_chunk(g + 1, use);
                         continue;
                     }
                     CF_STAMP(0, pidx, 1);
@@ -367,11 +408,6 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
 #pragma unroll
                     for (int combo = 0; combo < 3; ++combo) {              // hi*hi + hi*lo (A from TMEM) + lo*hi (A from smem)
                         const uint32_t bs = combo == 1 ? b_lo_s : b_hi_s;
-                        if (combo == 2 && c + 1 < NCH) {
-                            // the next chunk's barrier round trip hides behind the MMAs queued so far
-                            CF_STAMP(0, pidx + 1, 0);
-                            wait_chunk(g + 1, use + 1);
-                        }
 #pragma unroll
                         for (int ks = 0; ks < TC_K / 16; ++ks) {
                             // fp16 K-major no-swizzle: core matrix = 8 rows x 8 halfs (128 B); B: 14 row groups per K chunk,
@@ -416,7 +452,40 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
             }
             return x;
         };
+        // edge attributes [emb | node B | node C (+ C2) | 1 | 0 0 0] of this thread's edge (zeros for rows beyond the tile)
+        auto load_attr = [&](const Idx& x, float (&at)[64]) {
+            if (x.src >= 0) {
+                const float4* pe = reinterpret_cast<const float4*>(a.emb + (size_t)x.ce * 20);
+                const float2* pb = reinterpret_cast<const float2*>(a.tb + (size_t)x.ib * a.strideB);
+                const float2* pc = reinterpret_cast<const float2*>(a.tc + (size_t)x.ic * a.strideC);
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    const float4 v = __ldg(pe + q);
+                    at[4 * q] = v.x; at[4 * q + 1] = v.y; at[4 * q + 2] = v.z; at[4 * q + 3] = v.w;
+                }
+#pragma unroll
+                for (int q = 0; q < 10; ++q) {
+                    const float2 vb = __ldg(pb + q), vc = __ldg(pc + q);
+                    at[20 + 2 * q] = vb.x; at[21 + 2 * q] = vb.y;
+                    at[40 + 2 * q] = vc.x; at[41 + 2 * q] = vc.y;
+                }
+                if (x.ic2 >= 0) {
+                    const float2* pc2 = reinterpret_cast<const float2*>(a.tc + (size_t)x.ic2 * a.strideC);
+#pragma unroll
+                    for (int q = 0; q < 10; ++q) {
+                        const float2 vc = __ldg(pc2 + q);
+                        at[40 + 2 * q] += vc.x; at[41 + 2 * q] += vc.y;
+                    }
+                }
+                at[60] = 1.0f; at[61] = 0.f; at[62] = 0.f; at[63] = 0.f;       // k = 60 multiplies the bias row of W1aug
+            } else {
+#pragma unroll
+                for (int q = 0; q < 64; ++q) at[q] = 0.f;
+            }
+        };
         Idx ix = fetch((int)blockIdx.x);
+        float at[64];                                                        // loaded one pair ahead (before the previous reduce)
+        load_attr(ix, at);
         for (int pi = 0; pi < my_pairs; ++pi) {
             const int pair = (int)blockIdx.x + pi * (int)gridDim.x;
             const int ntile = (2 * pair + 1 < n_tiles) ? 2 : 1;
@@ -456,77 +525,18 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
             };
             // ---- prologue 1: edge attributes [emb | node B | node C] -> layer-1 A operand ----
             float rs1 = 0.f;
-            if (active) {
-                float at[64];
-                if (valid) {
-                    const float4* pe = reinterpret_cast<const float4*>(a.emb + (size_t)ix.ce * 20);
-                    const float2* pb = reinterpret_cast<const float2*>(a.tb + (size_t)ix.ib * a.strideB);
-                    const float2* pc = reinterpret_cast<const float2*>(a.tc + (size_t)ix.ic * a.strideC);
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) {
-                        const float4 v = __ldg(pe + q);
-                        at[4 * q] = v.x; at[4 * q + 1] = v.y; at[4 * q + 2] = v.z; at[4 * q + 3] = v.w;
-                    }
-#pragma unroll
-                    for (int q = 0; q < 10; ++q) {
-                        const float2 vb = __ldg(pb + q), vc = __ldg(pc + q);
-                        at[20 + 2 * q] = vb.x; at[21 + 2 * q] = vb.y;
-                        at[40 + 2 * q] = vc.x; at[41 + 2 * q] = vc.y;
-                    }
-                    if (ix.ic2 >= 0) {
-                        const float2* pc2 = reinterpret_cast<const float2*>(a.tc + (size_t)ix.ic2 * a.strideC);
-#pragma unroll
-                        for (int q = 0; q < 10; ++q) {
-                            const float2 vc = __ldg(pc2 + q);
-                            at[40 + 2 * q] += vc.x; at[41 + 2 * q] += vc.y;
-                        }
-                    }
-                    at[60] = 1.0f; at[61] = 0.f; at[62] = 0.f; at[63] = 0.f;   // k = 60 multiplies the bias row of W1aug
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 64; ++q) at[q] = 0.f;
-                }
-                rs1 = put_operand(at) * a.inv_w1scale;
-            }
+            if (active) rs1 = put_operand(at) * a.inv_w1scale;
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) tc_mbar_arrive(&a_ready[0]);                    // layer-1 operands in place
             CF_STAMP(1, 50, 1);
-            // ---- prologue 2 (under the first MMAs): gathered node rows -> smem (warp-cooperative, coalesced), SH -> registers,
-            //      seg_ptr of the pair's nodes -> smem for the epilogue ----
+            // ---- prologue 2 (under the hidden-layer MMA): seg_ptr of the pair's nodes -> smem for the epilogue, SH -> registers,
+            //      indices of the next pair (their round trips hide behind this pair) ----
             for (int i = tid; i <= ix.n_hi - ix.n_lo; i += CF_WORKERS) node_seg[i] = a.seg_ptr[ix.n_lo + i];
-            if (active) {
-                constexpr int NC = (Cfg::D_IN + 31) / 32;
-#pragma unroll 1
-                for (int r0 = 0; r0 < 32; r0 += CF_XB) {                      // CF_XB rows = up to 4 CF_XB coalesced loads in flight
-                    float v[CF_XB][NC];
 #pragma unroll
-                    for (int j = 0; j < CF_XB; ++j) {
-                        const int sr = __shfl_sync(0xffffffffu, ix.src, r0 + j);
-                        const float* srow = a.node_in + (size_t)(sr < 0 ? 0 : sr) * Cfg::D_IN;
-#pragma unroll
-                        for (int k = 0; k < NC; ++k) {
-                            const int c = 32 * k + lane;
-                            v[j][k] = (sr >= 0 && c < Cfg::D_IN) ? __ldg(srow + c) : 0.f;
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < CF_XB; ++j) {
-                        float* dst = xs + (size_t)(tid - lane + r0 + j) * S::XS;
-#pragma unroll
-                        for (int k = 0; k < NC; ++k) {
-                            const int c = 32 * k + lane;
-                            if (c < Cfg::D_IN) dst[c] = v[j][k];
-                        }
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < Cfg::SH_USED; ++i) shv[i] = valid ? __ldg(a.sh + (size_t)ix.ce * a.sh_stride + i) : 0.f;
-            } else {
-#pragma unroll
-                for (int i = 0; i < Cfg::SH_USED; ++i) shv[i] = 0.f;
-            }
-            __syncwarp();
+            for (int i = 0; i < Cfg::SH_USED; ++i) shv[i] = (active && valid) ? __ldg(a.sh + (size_t)ix.ce * a.sh_stride + i) : 0.f;
+            Idx nx = ix;
+            if (pi + 1 < my_pairs) nx = fetch(pair + (int)gridDim.x);
             // ---- prologue 3: hidden activations h = ReLU(D1) from tensor memory -> layer-2 A operand ----
             float rs = 0.f;
             if (active) {
@@ -555,30 +565,46 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
             // the power-of-two operand scales are undone exactly by scaling the spherical harmonics (Z is linear in them)
 #pragma unroll
             for (int i = 0; i < Cfg::SH_USED; ++i) shv[i] *= rs;
-            // indices of the next pair: their round trips hide behind the main loop
-            Idx nx = ix;
-            if (pi + 1 < my_pairs) nx = fetch(pair + (int)gridDim.x);
-            // ---- main loop: weights from TMEM, contraction on CUDA cores ----
-            float acc[Cfg::D_OUT];
+            // ---- prologue 4 (under the first chunk's MMAs): gathered node rows -> smem, warp-cooperative (lanes walk a row:
+            //      coalesced in global memory, conflict-free in the odd-stride smem rows), 32 rows = 4 x 32 loads in flight ----
+            if (active) {
+                constexpr int NC = (Cfg::D_IN + 31) / 32;
+                float v[32][NC];
 #pragma unroll
-            for (int d = 0; d < Cfg::D_OUT; ++d) acc[d] = 0.f;
+                for (int j = 0; j < 32; ++j) {
+                    const int sr = __shfl_sync(0xffffffffu, ix.src, j);
+                    const float* srow = a.node_in + (size_t)(sr < 0 ? 0 : sr) * Cfg::D_IN;
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) {
+                        const int c = 32 * k + lane;
+                        v[j][k] = (sr >= 0 && c < Cfg::D_IN) ? __ldg(srow + c) : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float* dst = xs + (size_t)(tid - lane + j) * S::XS;
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) {
+                        const int c = 32 * k + lane;
+                        if (c < Cfg::D_IN) dst[c] = v[j][k];
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- main loop: weights from TMEM, contraction on CUDA cores ----
+            float2 acc[Cfg::D_OUT / 2];
+#pragma unroll
+            for (int d = 0; d < Cfg::D_OUT / 2; ++d) acc[d] = make_float2(0.f, 0.f);
             cf_paths<Cfg, 0, PROBE>(lane_base, t_full, t_empty, item, tile, ntile, active, xrow, shv, acc, lane, pi == 1, item, a_dbg);
             CF_STAMP(1, 50, 2);
             // ---- epilogue: per-edge results -> smem (aliases the node rows), segmented mean + BatchNorm + residual ----
             cf_bar_workers();                                              // every worker is done with its node row
             float* stg = xs;
             if (active) {
-#pragma unroll
-                for (int q = 0; q < S::OQ; ++q) {
-                    float4 v;
-                    v.x = 4 * q < Cfg::D_OUT ? acc[4 * q < Cfg::D_OUT ? 4 * q : 0] : 0.f;
-                    v.y = 4 * q + 1 < Cfg::D_OUT ? acc[4 * q + 1 < Cfg::D_OUT ? 4 * q + 1 : 0] : 0.f;
-                    v.z = 4 * q + 2 < Cfg::D_OUT ? acc[4 * q + 2 < Cfg::D_OUT ? 4 * q + 2 : 0] : 0.f;
-                    v.w = 4 * q + 3 < Cfg::D_OUT ? acc[4 * q + 3 < Cfg::D_OUT ? 4 * q + 3 : 0] : 0.f;
-                    *reinterpret_cast<float4*>(stg + (size_t)tid * S::OS + 4 * q) = v;
-                }
+                cf_stage_row<Cfg, 0, S::OQ>(acc, stg + (size_t)tid * S::OS);
             }
             cf_bar_workers();
+            load_attr(nx, at);             // next pair's attributes (unconditional: `at` must not stay live across the main loop)
             CF_STAMP(1, 51, 0);
             {
                 const int e_lo = node_seg[0], e_mid = node_seg[ix.n_mid - ix.n_lo];

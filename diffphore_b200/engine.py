@@ -312,121 +312,127 @@ def _pair_arrays(g):
 
 
 class PackedBatch:
-    """Flattened device arrays for B graphs (PyG-Batch-like; graph g = pair g // samples, sample g % samples)."""
+    """Flattened device arrays for B graphs (PyG-Batch-like; graph g = pair g // samples, sample g % samples).
+
+    Only per-PAIR arrays cross the PCIe bus; the `samples` copies of every pair (identical topology and features, the
+    reference builds them with copy.deepcopy, inference.py:196) are expanded on the device with index arithmetic."""
 
     def __init__(self, graphs, samples_per_graph, weights, device):
         S = samples_per_graph
         pa = [_pair_arrays(g) for g in graphs]
-        B = len(pa) * S
+        Np = len(pa)
+        B = Np * S
         self.B, self.S, self.device = B, S, device = B, S, torch.device(device)
-        rep = lambda arrs: np.concatenate([np.tile(a, (S,) + (1,) * (a.ndim - 1)) for a in arrs], 0)
-        n_per = np.repeat([p.n for p in pa], S)
-        P_per = np.repeat([p.P for p in pa], S)
-        nrot_per = np.repeat([len(p.rot_u) for p in pa], S)
-        lig_ptr = np.concatenate([[0], np.cumsum(n_per)]).astype(np.int64)
-        ph_ptr = np.concatenate([[0], np.cumsum(P_per)]).astype(np.int64)
-        rot_ptr = np.concatenate([[0], np.cumsum(nrot_per)]).astype(np.int64)
-        self.n_lig, self.n_ph, self.n_rot = int(lig_ptr[-1]), int(ph_ptr[-1]), int(rot_ptr[-1])
-        self.max_atoms, self.max_rot = int(n_per.max()), int(nrot_per.max())
-        self.n_per, self.P_per, self.nrot_per = n_per, P_per, nrot_per
-        gi = 0
-        bond_ptr, bond_dst, bond_type, rot_u, rot_v, pp_src, pp_dst, pp_ptr = [], [], [], [], [], [], [], []
-        cl, cp, cptr, masks, moff = [], [], [0], [], [0]
-        cl_t, cp_t, perm_t, cseg_ph = [], [], [], [0]
-        e_off = pp_off = c_off = 0
-        tl_lig, tl_ph, tl_pp = [], [], []          # node-aligned tiles of the static edge sets (dp_conv_fused)
-        for p in pa:
-            t_lig, t_ph = greedy_tiles([p.P] * p.n), greedy_tiles([p.n] * p.P)
-            t_pp = greedy_tiles(np.diff(p.pp_ptr))
-            for s in range(S):
-                a0, p0 = int(lig_ptr[gi]), int(ph_ptr[gi])
-                for lst, t, off in ((tl_lig, t_lig, a0), (tl_ph, t_ph, p0), (tl_pp, t_pp, p0)):
-                    lst.append(None if t is None else np.asarray(t, np.int64) + off)
-                bond_ptr.append(p.bond_ptr[:-1] + e_off)
-                bond_dst.append(p.bond_dst + a0)
-                bond_type.append(p.bond_type)
-                e_off += len(p.bond_dst)
-                rot_u.append(p.rot_u + a0)
-                rot_v.append(p.rot_v + a0)
-                pp_src.append(p.pp_src + p0)
-                pp_dst.append(p.pp_dst + p0)
-                pp_ptr.append(p.pp_ptr[:-1] + pp_off)
-                pp_off += len(p.pp_src)
-                # cross edges sorted by (lig, phore)  (smp:770-781)
-                a = np.repeat(np.arange(p.n), p.P)
-                q = np.tile(np.arange(p.P), p.n)
-                cl.append(a + a0)
-                cp.append(q + p0)
-                # transposed order (phore-major) for the lig->phore convolutions
-                qt = np.repeat(np.arange(p.P), p.n)
-                at = np.tile(np.arange(p.n), p.P)
-                cl_t.append(at + a0)
-                cp_t.append(qt + p0)
-                perm_t.append(c_off + at * p.P + qt)
-                c_off += p.n * p.P
-                cptr.append(c_off)
-                masks.append(p.mask.reshape(-1))
-                moff.append(moff[-1] + p.mask.size)
-                gi += 1
         self.h2d_bytes = 0
 
-        def up(t):
+        def up(a):
+            t = torch.from_numpy(np.ascontiguousarray(a))
             self.h2d_bytes += t.numel() * t.element_size()
             if device.type == 'cuda':
                 return t.pin_memory().to(device, non_blocking=True)
             return t.to(device)
 
-        i32 = lambda a: up(torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.int32))))
-        f32 = lambda a: up(torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32))))
-        cat = lambda l, dt: np.concatenate(l).astype(dt) if len(l) else np.zeros(0, dt)
-        self.lig_ptr, self.ph_ptr, self.rot_ptr = i32(lig_ptr), i32(ph_ptr), i32(rot_ptr)
-        self.lig_batch = i32(np.repeat(np.arange(B), n_per))
-        self.bond_ptr = i32(np.concatenate([cat(bond_ptr, np.int64), [e_off]]))
-        self.bond_dst, self.bond_type = i32(cat(bond_dst, np.int64)), i32(cat(bond_type, np.int64))
-        self.n_bond = e_off
-        self.rot_u, self.rot_v = i32(cat(rot_u, np.int64)), i32(cat(rot_v, np.int64))
-        self.pp_src, self.pp_dst = i32(cat(pp_src, np.int64)), i32(cat(pp_dst, np.int64))
-        self.pp_ptr = i32(np.concatenate([cat(pp_ptr, np.int64), [pp_off]]))
-        self.n_pp = pp_off
-        self.cross_lig, self.cross_ph, self.cross_ptr = i32(cat(cl, np.int64)), i32(cat(cp, np.int64)), i32(cptr)
-        self.cross_lig_t, self.cross_ph_t, self.cross_perm_t = i32(cat(cl_t, np.int64)), i32(cat(cp_t, np.int64)), i32(cat(perm_t, np.int64))
-        self.n_cross = c_off
-        # CSR of cross edges by ligand atom (canonical order) and by phore node (transposed order)
-        self.cross_seg_lig = i32(np.concatenate([[0], np.cumsum(np.repeat(P_per, n_per))]))
-        self.cross_seg_ph = i32(np.concatenate([[0], np.cumsum(np.repeat(n_per, P_per))]))
-        def tiles(lst, n_nodes):
-            if any(t is None for t in lst):
-                return None                     # a node with > 128 edges: this edge set stays on the unfused kernels
-            t = np.concatenate(lst + [np.asarray([n_nodes], np.int64)])
-            return (i32(t), None, len(t) - 1)
+        cat = lambda key, dt: up(np.concatenate([np.asarray(getattr(q, key)).reshape(-1) if np.asarray(getattr(q, key)).ndim == 1
+                                                 else np.asarray(getattr(q, key)) for q in pa]).astype(dt))
+        cnt = lambda vals: up(np.asarray(vals, dtype=np.int64))
+        # ---- per-pair element counts (host) and their device copies
+        n_p, P_p = np.asarray([q.n for q in pa]), np.asarray([q.P for q in pa])
+        nrot_p, nb_p, npp_p = (np.asarray([len(q.rot_u) for q in pa]), np.asarray([len(q.bond_dst) for q in pa]),
+                               np.asarray([len(q.pp_src) for q in pa]))
+        t_lig = [greedy_tiles([q.P] * q.n) for q in pa]
+        t_ph = [greedy_tiles([q.n] * q.P) for q in pa]
+        t_pp = [greedy_tiles(np.diff(q.pp_ptr)) for q in pa]
+        self.n_per, self.P_per, self.nrot_per = np.repeat(n_p, S), np.repeat(P_p, S), np.repeat(nrot_p, S)
+        self.n_lig, self.n_ph, self.n_rot = int(n_p.sum()) * S, int(P_p.sum()) * S, int(nrot_p.sum()) * S
+        self.n_bond, self.n_pp, self.n_cross = int(nb_p.sum()) * S, int(npp_p.sum()) * S, int((n_p * P_p).sum()) * S
+        self.max_atoms, self.max_rot = int(n_p.max()), int(nrot_p.max())
+        k = weights.cfg['max_neighbors']
+        self.ll_cap = int(self.n_bond + S * np.sum(n_p * np.minimum(n_p - 1, k + 1)))
+        self.tor_cap = int(S * np.sum(nrot_p * np.minimum(n_p, k)))
+        i64 = dict(dtype=torch.int64, device=device)
+        pair_of_graph = torch.arange(Np, **i64).repeat_interleave(S)
 
-        self.tiles_cross_lig, self.tiles_cross_ph = tiles(tl_lig, self.n_lig), tiles(tl_ph, self.n_ph)
-        self.tiles_pp = tiles(tl_pp, self.n_ph)
-        self.mask = up(torch.from_numpy(cat(masks, np.uint8)))
-        self.mask_off = up(torch.from_numpy(np.asarray(moff[:-1], dtype=np.int64)))
+        def excl(c):                                    # exclusive prefix sum with the total appended: [len + 1]
+            return torch.cat([torch.zeros(1, **i64), torch.cumsum(c, 0)])
+
+        class Level:
+            """Expansion of one per-pair element kind (atoms, bonds, ...) over the samples: for every expanded element its
+            graph, its index in the compact (per-pair) array and its index inside its graph."""
+            def __init__(lv, m_pair):
+                lv.m_pair = cnt(m_pair)
+                lv.cbase = excl(lv.m_pair)                              # compact base of every pair
+                lv.m_graph = lv.m_pair[pair_of_graph]
+                lv.gbase = excl(lv.m_graph)                             # expanded base of every graph [B + 1]
+                lv.total = int(np.sum(m_pair)) * S
+                lv.graph = torch.arange(B, **i64).repeat_interleave(lv.m_graph, output_size=lv.total)
+                lv.local = torch.arange(lv.total, **i64) - lv.gbase[lv.graph]
+                lv.src = lv.cbase[pair_of_graph[lv.graph]] + lv.local
+
+        atoms, phs, bonds, rots, pps = Level(n_p), Level(P_p), Level(nb_p), Level(nrot_p), Level(npp_p)
+        i32 = lambda t: t.to(torch.int32).contiguous()
+        a0, p0 = atoms.gbase, phs.gbase                                # first atom / phore node of every graph
+        self.lig_ptr, self.ph_ptr, self.rot_ptr = i32(a0), i32(p0), i32(rots.gbase)
+        self.lig_batch = i32(atoms.graph)
+        # ---- bonds (CSR by source atom), rotatable bonds, phore-phore edges (CSR by source node)
+        bptr_c = cat_ptr = up(np.concatenate([q.bond_ptr[:-1] for q in pa]).astype(np.int64))
+        self.bond_ptr = i32(torch.cat([bptr_c[atoms.src] + bonds.gbase[atoms.graph], bonds.gbase[-1:]]))
+        self.bond_dst = i32(cat('bond_dst', np.int64)[bonds.src] + a0[bonds.graph])
+        self.bond_type = i32(cat('bond_type', np.int64)[bonds.src])
+        self.rot_u = i32(cat('rot_u', np.int64)[rots.src] + a0[rots.graph])
+        self.rot_v = i32(cat('rot_v', np.int64)[rots.src] + a0[rots.graph])
+        self.pp_src = i32(cat('pp_src', np.int64)[pps.src] + p0[pps.graph])
+        self.pp_dst = i32(cat('pp_dst', np.int64)[pps.src] + p0[pps.graph])
+        pptr_c = up(np.concatenate([q.pp_ptr[:-1] for q in pa]).astype(np.int64))
+        self.pp_ptr = i32(torch.cat([pptr_c[phs.src] + pps.gbase[phs.graph], pps.gbase[-1:]]))
+        # ---- complete bipartite cross edges, sorted by (lig, phore) (smp:770-781) and the phore-major transposed order
+        n_g, P_g = atoms.m_graph, phs.m_graph
+        cbase = excl(n_g * P_g)
+        self.cross_ptr = i32(cbase)
+        cg = torch.arange(B, **i64).repeat_interleave(n_g * P_g, output_size=self.n_cross)
+        cl_ = torch.arange(self.n_cross, **i64) - cbase[cg]
+        ng, Pg = n_g[cg], P_g[cg]
+        self.cross_lig, self.cross_ph = i32(a0[cg] + cl_ // Pg), i32(p0[cg] + cl_ % Pg)
+        at, qt = cl_ % ng, cl_ // ng
+        self.cross_lig_t, self.cross_ph_t = i32(a0[cg] + at), i32(p0[cg] + qt)
+        self.cross_perm_t = i32(cbase[cg] + at * Pg + qt)
+        # CSR of cross edges by ligand atom (canonical order) and by phore node (transposed order)
+        self.cross_seg_lig = i32(excl(P_g[atoms.graph]))
+        self.cross_seg_ph = i32(excl(n_g[phs.graph]))
+        del cg, cl_, ng, Pg, at, qt
+
+        # ---- node-aligned tiles of the static edge sets (dp_conv_fused); a node with > 128 edges: unfused kernels
+        def tiles(per_pair, node_base, n_nodes):
+            if any(t is None for t in per_pair):
+                return None
+            lv = Level(np.asarray([len(t) for t in per_pair]))
+            tn = up(np.concatenate([np.asarray(t, np.int64) for t in per_pair]))[lv.src] + node_base[lv.graph]
+            return (i32(torch.cat([tn, torch.full((1,), n_nodes, **i64)])), None, lv.total)
+
+        self.tiles_cross_lig, self.tiles_cross_ph = tiles(t_lig, a0, self.n_lig), tiles(t_ph, p0, self.n_ph)
+        self.tiles_pp = tiles(t_pp, p0, self.n_ph)
+        # ---- mask_rotate rows (uint8) and their per-graph byte offsets
+        msk = Level(nrot_p * n_p)
+        self.mask = up(np.concatenate([q.mask.reshape(-1) for q in pa]).astype(np.uint8))[msk.src].contiguous() \
+            if msk.total else torch.zeros(0, dtype=torch.uint8, device=device)
+        self.mask_off = msk.gbase[:-1].contiguous()
         self.lig_arange = torch.arange(self.n_lig, dtype=torch.int32, device=device)
-        # node-level tensors
-        self.pos = f32(rep([p.pos for p in pa]))
-        self.norm = f32(rep([p.norm for p in pa]))
-        self.phorefp, self.na1, self.na2 = f32(rep([p.phorefp for p in pa])), f32(rep([p.na1 for p in pa])), f32(rep([p.na2 for p in pa]))
-        self.ppos, self.pnorm, self.ptype = f32(rep([p.ppos for p in pa])), f32(rep([p.pnorm for p in pa])), f32(rep([p.ptype for p in pa]))
-        x = up(torch.from_numpy(rep([p.x for p in pa])))
-        px = f32(rep([p.px for p in pa]))
-        # static parts of the AtomEncoders (setup-time gathers; smp:64-73)
+        # ---- node-level features
+        f32c = lambda key: up(np.concatenate([getattr(q, key) for q in pa], 0).astype(np.float32))
+        self.pos, self.norm = f32c('pos')[atoms.src].contiguous(), f32c('norm')[atoms.src].contiguous()
+        self.phorefp, self.na1, self.na2 = (f32c(kk)[atoms.src].contiguous() for kk in ('phorefp', 'na1', 'na2'))
+        self.ppos, self.pnorm, self.ptype = (f32c(kk)[phs.src].contiguous() for kk in ('ppos', 'pnorm', 'ptype'))
+        # static parts of the AtomEncoders (setup-time gathers; smp:64-73), evaluated once per pair
         w = weights
-        ls = torch.zeros(self.n_lig, 20, device=device)
+        x, px = up(np.concatenate([q.x for q in pa], 0).astype(np.int64)), f32c('px')
+        ls = torch.zeros(x.shape[0], 20, device=device)
         for i in range(16):
             ls = ls + w.lig_tables[i][x[:, i]]
-        ps = torch.zeros(self.n_ph, 20, device=device)
+        ps = torch.zeros(px.shape[0], 20, device=device)
         for i in range(3):
             ps = ps + w.ph_tables[i][px[:, i].long()]
         # explicit products in a fixed order (a cuBLAS matmul may pick a size-dependent kernel => batch-composition-dependent rounding)
         ps = ps + px[:, 3:4] * w.ph_lin_w[:, 0][None, :] + px[:, 4:5] * w.ph_lin_w[:, 1][None, :]
-        self.lig_static, self.ph_static = ls.contiguous(), ps.contiguous()
-        # capacities of the dynamic edge sets
-        k = weights.cfg['max_neighbors']
-        self.ll_cap = int(e_off + np.sum(n_per * np.minimum(n_per - 1, k + 1)))
-        self.tor_cap = int(np.sum(nrot_per * np.minimum(n_per, k)))
+        self.lig_static, self.ph_static = ls[atoms.src].contiguous(), ps[phs.src].contiguous()
 
 
 class Workspace:
