@@ -126,7 +126,7 @@ def main():
         if rank != 0:
             return
         vals = []
-        n_pairs, samples = 1, 8
+        n_pairs, samples = 8, 8                                  # ~12 s of CPU work per bench step
         for _ in range(args.warmup if args.warmup < 2 else 1):
             cpu_reference_rate(1, 2, cores, steps=2)
         t0 = time.time()
@@ -228,9 +228,10 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r, dt = cpu_reference_rate(1, 8, cores)
+        r, dt = cpu_reference_rate(8, 8, cores)
         cpu = {'value': r, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
-               'sample': f'1 pair x 8 samples x {INF_STEPS} steps of the cfg2 shape ({dt:.1f} s of CPU work, oracle port)'}
+               'sample': f'8 pairs x 8 samples x {INF_STEPS} steps of the cfg2 shape ({dt:.1f} s of CPU work, oracle port, '
+                         f'torch.set_num_threads({cores}))'}
     if rank == 0:
         print(json.dumps({'metric': 'denoised samples/sec (20-step)', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
                           'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,

@@ -463,11 +463,22 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
                     const float4 v = __ldg(pe + q);
                     at[4 * q] = v.x; at[4 * q + 1] = v.y; at[4 * q + 2] = v.z; at[4 * q + 3] = v.w;
                 }
+                if (((a.strideB | a.strideC) & 3) == 0) {                     // 16-byte aligned node rows: half the load instructions
+                    const float4* pb4 = reinterpret_cast<const float4*>(pb);
+                    const float4* pc4 = reinterpret_cast<const float4*>(pc);
 #pragma unroll
-                for (int q = 0; q < 10; ++q) {
-                    const float2 vb = __ldg(pb + q), vc = __ldg(pc + q);
-                    at[20 + 2 * q] = vb.x; at[21 + 2 * q] = vb.y;
-                    at[40 + 2 * q] = vc.x; at[41 + 2 * q] = vc.y;
+                    for (int q = 0; q < 5; ++q) {
+                        const float4 vb = __ldg(pb4 + q), vc = __ldg(pc4 + q);
+                        at[20 + 4 * q] = vb.x; at[21 + 4 * q] = vb.y; at[22 + 4 * q] = vb.z; at[23 + 4 * q] = vb.w;
+                        at[40 + 4 * q] = vc.x; at[41 + 4 * q] = vc.y; at[42 + 4 * q] = vc.z; at[43 + 4 * q] = vc.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 10; ++q) {
+                        const float2 vb = __ldg(pb + q), vc = __ldg(pc + q);
+                        at[20 + 2 * q] = vb.x; at[21 + 2 * q] = vb.y;
+                        at[40 + 2 * q] = vc.x; at[41 + 2 * q] = vc.y;
+                    }
                 }
                 if (x.ic2 >= 0) {
                     const float2* pc2 = reinterpret_cast<const float2*>(a.tc + (size_t)x.ic2 * a.strideC);

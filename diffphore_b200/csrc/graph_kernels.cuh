@@ -465,7 +465,10 @@ tor_fill_kernel(const float* __restrict__ lpos, const int* __restrict__ lig_ptr,
                 int* __restrict__ e_atom, int* __restrict__ e_u, int* __restrict__ e_v, float* __restrict__ e_emb,
                 float* __restrict__ e_sh) {
     __shared__ int soff[LG_MAXN + 1];
+    __shared__ float sw0[400], sw3[400], sb0[20], sb3[20];
     const int g = blockIdx.x, a0 = lig_ptr[g], n = lig_ptr[g + 1] - a0, r0 = rot_ptr[g], nr = rot_ptr[g + 1] - r0;
+    for (int i = threadIdx.x; i < 400; i += blockDim.x) { sw0[i] = sw.final_edge.w0[i]; sw3[i] = sw.final_edge.w3[i]; }
+    for (int i = threadIdx.x; i < 20; i += blockDim.x) { sb0[i] = sw.final_edge.b0[i]; sb3[i] = sw.final_edge.b3[i]; }
     if (threadIdx.x == 0) {
         int run = gstart[g];
         for (int r = 0; r < nr; ++r) { soff[r] = run; run += deg[r0 + r]; }
@@ -475,34 +478,42 @@ tor_fill_kernel(const float* __restrict__ lpos, const int* __restrict__ lig_ptr,
     for (int r = threadIdx.x; r < nr; r += blockDim.x) seg_ptr[r0 + r] = soff[r];
     if (g == n_graphs - 1 && threadIdx.x == 0) seg_ptr[r0 + nr] = soff[nr];
     const float r2 = c_dp.lig_radius * c_dp.lig_radius;
+    // topology: thread per rotatable bond (torch_cluster.radius: atoms within 5 A of the bond centre, lowest indices first)
     for (int r = threadIdx.x; r < nr; r += blockDim.x) {
         const int u = rot_u[r0 + r], v = rot_v[r0 + r];
         const float cx = (lpos[u * 3] + lpos[v * 3]) / 2, cy = (lpos[u * 3 + 1] + lpos[v * 3 + 1]) / 2, cz = (lpos[u * 3 + 2] + lpos[v * 3 + 2]) / 2;
-        float b2[9];
-        dp_sh9(lpos[v * 3] - lpos[u * 3], lpos[v * 3 + 1] - lpos[u * 3 + 1], lpos[v * 3 + 2] - lpos[u * 3 + 2], b2);   // Y2 = b2[4..8]
         int o = soff[r], d = 0;
         for (int i = 0; i < n && d < c_dp.max_neighbors; ++i) {
             const int a = a0 + i;
             if (dp_dist2(cx, cy, cz, lpos[a * 3], lpos[a * 3 + 1], lpos[a * 3 + 2]) < r2) {
-                const float vx = lpos[a * 3] - cx, vy = lpos[a * 3 + 1] - cy, vz = lpos[a * 3 + 2] - cz;
-                float rbf[20], h[20], sh[9], o7[8];
-                dp_rbf20(sqrtf(vx * vx + vy * vy + vz * vz), DP_RBF_LIG, rbf);
-                for (int q = 0; q < 20; ++q) {
-                    float acc = sw.final_edge.b0[q];
-#pragma unroll
-                    for (int c = 0; c < 20; ++c) acc = fmaf(rbf[c], sw.final_edge.w0[q * 20 + c], acc);
-                    h[q] = acc;
-                }
-                dp_mlp20_out(h, sw.final_edge.w3, sw.final_edge.b3, e_emb + (size_t)o * 20);
-                dp_sh9(vx, vy, vz, sh);
-                dp_fulltp7(sh, b2 + 4, o7);
-                o7[7] = 0.f;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) e_sh[(size_t)o * 8 + k] = o7[k];
                 e_atom[o] = a; e_u[o] = u; e_v[o] = v;
                 ++o; ++d;
             }
         }
+    }
+    __syncthreads();
+    // features: thread per edge (the 20 -> 20 -> 20 embedding MLP dominates; all 128 threads busy instead of one per bond)
+    for (int e = soff[0] + threadIdx.x; e < soff[nr]; e += blockDim.x) {
+        const int a = e_atom[e], u = e_u[e], v = e_v[e];
+        const float cx = (lpos[u * 3] + lpos[v * 3]) / 2, cy = (lpos[u * 3 + 1] + lpos[v * 3 + 1]) / 2, cz = (lpos[u * 3 + 2] + lpos[v * 3 + 2]) / 2;
+        float b2[9];
+        dp_sh9(lpos[v * 3] - lpos[u * 3], lpos[v * 3 + 1] - lpos[u * 3 + 1], lpos[v * 3 + 2] - lpos[u * 3 + 2], b2);   // Y2 = b2[4..8]
+        const float vx = lpos[a * 3] - cx, vy = lpos[a * 3 + 1] - cy, vz = lpos[a * 3 + 2] - cz;
+        float rbf[20], h[20], sh[9], o7[8];
+        dp_rbf20(sqrtf(vx * vx + vy * vy + vz * vz), DP_RBF_LIG, rbf);
+#pragma unroll 4
+        for (int q = 0; q < 20; ++q) {
+            float acc = sb0[q];
+#pragma unroll
+            for (int c = 0; c < 20; ++c) acc = fmaf(rbf[c], sw0[q * 20 + c], acc);
+            h[q] = acc;
+        }
+        dp_mlp20_out(h, sw3, sb3, e_emb + (size_t)e * 20);
+        dp_sh9(vx, vy, vz, sh);
+        dp_fulltp7(sh, b2 + 4, o7);
+        o7[7] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) e_sh[(size_t)e * 8 + k] = o7[k];
     }
 }
 
