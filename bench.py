@@ -37,6 +37,22 @@ def peaks():
         return 6650.0, 'fallback'
 
 
+def ncu_traffic(tag):
+    """dram read + write bytes of the first `tag` launch in the committed ncu --set full summary (None if absent)."""
+    try:
+        import csv
+        rows = list(csv.reader(open(os.path.join(ROOT, 'profiles', 'ncu_conv_fused_r1_final.csv'))))
+        h, units = rows[0], rows[1]
+        ir, iw = h.index('dram__bytes_read.sum'), h.index('dram__bytes_write.sum')
+        scale = {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1.0}
+        for r in rows[2:]:
+            if tag in r[0]:
+                return float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+    except Exception:
+        pass
+    return None
+
+
 def tensor_peak():
     """Sustained dense bf16 cuBLAS throughput (the conv kernel is timed inside a seconds-long step)."""
     try:
@@ -205,7 +221,7 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms = float(tmax.item())
     value = n_samples_local * world / (ms / 1000.0)
-    roof = prof.roofline_fused(*tensor_peak(), peaks()[0]) or prof.roofline(*peaks())
+    roof = prof.roofline_fused(*tensor_peak(), peaks()[0], traffic_bytes=ncu_traffic('TpL3')) or prof.roofline(*peaks())
 
     # ---- end-to-end arm through the public API with host inputs
     e2e = None

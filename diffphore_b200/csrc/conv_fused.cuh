@@ -579,25 +579,42 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
             // ---- prologue 4 (under the first chunk's MMAs): gathered node rows -> smem, warp-cooperative (lanes walk a row:
             //      coalesced in global memory, conflict-free in the odd-stride smem rows), 32 rows = 4 x 32 loads in flight ----
             if (active) {
-                constexpr int NC = (Cfg::D_IN + 31) / 32;
-                float v[32][NC];
+                // lanes read VEC consecutive floats of a row (one 16- or 8-byte load per row and lane) and write them to the
+                // odd-stride smem row in a lane-rotated order, so that every scalar store instruction is bank-conflict free
+                constexpr int VEC = (Cfg::D_IN % 4 == 0) ? 4 : 2;
+                constexpr int NL = Cfg::D_IN / VEC;                         // active lanes per row (<= 32)
+                static_assert(Cfg::D_IN % VEC == 0 && NL <= 32, "row gather layout");
+                float v[32][VEC];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int sr = __shfl_sync(0xffffffffu, ix.src, j);
-                    const float* srow = a.node_in + (size_t)(sr < 0 ? 0 : sr) * Cfg::D_IN;
+                    const float* srow = a.node_in + (size_t)(sr < 0 ? 0 : sr) * Cfg::D_IN + VEC * lane;
+                    if (sr >= 0 && lane < NL) {
+                        if constexpr (VEC == 4) {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(srow));
+                            v[j][0] = t.x; v[j][1] = t.y; v[j][2] = t.z; v[j][3] = t.w;
+                        } else {
+                            const float2 t = __ldg(reinterpret_cast<const float2*>(srow));
+                            v[j][0] = t.x; v[j][1] = t.y;
+                        }
+                    } else {
 #pragma unroll
-                    for (int k = 0; k < NC; ++k) {
-                        const int c = 32 * k + lane;
-                        v[j][k] = (sr >= 0 && c < Cfg::D_IN) ? __ldg(srow + c) : 0.f;
+                        for (int i = 0; i < VEC; ++i) v[j][i] = 0.f;
                     }
                 }
+                const int rot = lane * VEC / 32;                            // lanes L and L + 32 / VEC would hit the same bank
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    float* dst = xs + (size_t)(tid - lane + j) * S::XS;
+                    float* dst = xs + (size_t)(tid - lane + j) * S::XS + VEC * lane;
+                    if (lane < NL) {
 #pragma unroll
-                    for (int k = 0; k < NC; ++k) {
-                        const int c = 32 * k + lane;
-                        if (c < Cfg::D_IN) dst[c] = v[j][k];
+                        for (int i = 0; i < VEC; ++i) {
+                            const int k = (i + rot) & (VEC - 1);
+                            float val = v[j][0];
+#pragma unroll
+                            for (int q = 1; q < VEC; ++q) val = (k == q) ? v[j][q] : val;
+                            dst[k] = val;
+                        }
                     }
                 }
             }
@@ -610,30 +627,39 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
             CF_STAMP(1, 50, 2);
             // ---- epilogue: per-edge results -> smem (aliases the node rows), segmented mean + BatchNorm + residual ----
             cf_bar_workers();                                              // every worker is done with its node row
+            CF_STAMP(1, 52, 0);
             float* stg = xs;
             if (active) {
                 cf_stage_row<Cfg, 0, S::OQ>(acc, stg + (size_t)tid * S::OS);
             }
+            CF_STAMP(1, 52, 1);
             cf_bar_workers();
+            CF_STAMP(1, 52, 2);
             load_attr(nx, at);             // next pair's attributes (unconditional: `at` must not stay live across the main loop)
             CF_STAMP(1, 51, 0);
             {
                 const int e_lo = node_seg[0], e_mid = node_seg[ix.n_mid - ix.n_lo];
                 const int items = (ix.n_hi - ix.n_lo) * S::OQ;
+                // residual / running-sum operand of item `it` (loads issued one iteration ahead of their use)
+                auto load_add = [&](int it, float (&add)[4]) {
+                    const int nl = it / S::OQ, q = it % S::OQ, node = ix.n_lo + nl;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int d = 4 * q + j;
+                        add[j] = 0.f;
+                        if (it < items && d < Cfg::D_OUT) {
+                            if (a.mode == 1) add[j] = (d < a.res_dim) ? __ldg(a.residual + (size_t)node * a.res_dim + d) : 0.0f;
+                            else if (a.mode == 2) add[j] = a.out[(size_t)node * Cfg::D_OUT + d];
+                        }
+                    }
+                };
+                float add[4], add_n[4];
+                load_add(tid, add);
                 for (int it = tid; it < items; it += CF_WORKERS) {
+                    load_add(it + CF_WORKERS, add_n);
                     const int nl = it / S::OQ, q = it % S::OQ, node = ix.n_lo + nl;
                     const int s0 = node_seg[nl], s1 = node_seg[nl + 1];
                     float* orow = a.out + (size_t)node * Cfg::D_OUT;
-                    float add[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {                            // residual / running sum: loads overlap the reduction
-                        const int d = 4 * q + j;
-                        add[j] = 0.f;
-                        if (d < Cfg::D_OUT) {
-                            if (a.mode == 1) add[j] = (d < a.res_dim) ? a.residual[(size_t)node * a.res_dim + d] : 0.0f;
-                            else if (a.mode == 2) add[j] = orow[d];
-                        }
-                    }
                     const int r0 = node < ix.n_mid ? s0 - e_lo : 128 + s0 - e_mid;
                     const float* sp = stg + (size_t)r0 * S::OS + 4 * q;
                     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -649,6 +675,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
                     for (int j = 0; j < 4; ++j) {
                         const int d = 4 * q + j;
                         if (d < Cfg::D_OUT) orow[d] = sv[j] * inv_deg * osc[d] + osh[d] + add[j];
+                        add[j] = add_n[j];
                     }
                 }
             }

@@ -52,29 +52,38 @@ class KernelTimer:
                           tflops=a['flops'] / a['sec'] / 1e12 if a['flops'] else None, total_ms=1e3 * a['sec'])
         return out
 
-    def roofline_fused(self, peak_tflops, peak_src, hbm_gbs):
-        """Aggregate over every dp_conv_fused launch (tensor-pipe bound; the weights never reach HBM).  `equiv_hbm_gbs`
-        is what the unfused dp_tp_scatter would have had to stream in the same time (SURVEY 8d algorithmic bytes)."""
-        tot_f = tot_s = tot_b = tot_mma = 0.0
-        n = 0
-        for kind, name, sec, E, m in self._resolved():
-            if kind == 'conv_fused':
-                tot_f += float(E) * (2.0 * (m['in_dim'] + 1) * m['hid'] + 2.0 * (m['hid'] + 1) * m['W'] + m['tp_flops'])
-                tot_mma += float(E) * 2.0 * 64 * (m['W'] * 1.12 + 64) * 3
-                tot_b += float(E) * (4 * m['W'] + 4 * m['d_in'] + 4 * 9 + 8) + m['n_out'] * 4 * m['d_out']
-                tot_s += sec
-                n += 1
-        if tot_s == 0:
+    def roofline_fused(self, peak_tflops, peak_src, hbm_gbs, dominant='lig3', traffic_bytes=None):
+        """Roofline of the dominant kernel = dp_conv_fused of the layer-3 ligand-ligand convolution (`dominant`; the largest
+        launch of the step), tensor-pipe bound: the weights never reach HBM.  `all_layers` aggregates every dp_conv_fused
+        launch of the timed region.  `equiv_hbm_*` is what the unfused dp_tp_scatter would have had to stream in the same
+        time (SURVEY 8d algorithmic bytes); `traffic_bytes` = dram read + write of one ncu --set full capture (per launch)."""
+        def agg(select):
+            f = s = b = mma = 0.0
+            n = 0
+            for kind, name, sec, E, m in self._resolved():
+                if kind == 'conv_fused' and select(name):
+                    f += float(E) * (2.0 * (m['in_dim'] + 1) * m['hid'] + 2.0 * (m['hid'] + 1) * m['W'] + m['tp_flops'])
+                    mma += float(E) * 2.0 * 64 * (m['W'] * 1.12 + 64) * 3
+                    b += float(E) * (4 * m['W'] + 4 * m['d_in'] + 4 * 9 + 8) + m['n_out'] * 4 * m['d_out']
+                    s += sec
+                    n += 1
+            if s == 0:
+                return None
+            return dict(achieved=f / s / 1e12, peak=peak_tflops, unit='TFLOP/s', frac=f / s / 1e12 / peak_tflops, launches=n,
+                        flops_per_launch=f / n, ms_per_launch=1e3 * s / n, issued_mma_tflops=mma / s / 1e12,
+                        issued_mma_frac=mma / s / 1e12 / peak_tflops, equiv_hbm_gbs=b / s / 1e9, equiv_hbm_frac=b / s / 1e9 / hbm_gbs)
+        dom, allk = agg(lambda nm: nm == dominant), agg(lambda nm: True)
+        if dom is None:
             return None
-        ach = tot_f / tot_s / 1e12
-        return dict(kernel='conv_fused_kernel (all layers)', bound='tensor', achieved=ach, peak=peak_tflops, unit='TFLOP/s',
-                    frac=ach / peak_tflops, traffic=None, peak_source=f'{peak_src} dense bf16 cuBLAS throughput (sustained)',
-                    launches=n, flops_per_launch=tot_f / n, ms_per_launch=1e3 * tot_s / n,
-                    issued_mma_tflops=tot_mma / tot_s / 1e12, issued_mma_frac=tot_mma / tot_s / 1e12 / peak_tflops,
-                    equiv_hbm_gbs=tot_b / tot_s / 1e9, equiv_hbm_frac=tot_b / tot_s / 1e9 / hbm_gbs,
-                    note='algorithmic FLOPs = E*(2*61*60 + 2*61*W + tp_flops) (both MLP layers + channel mixing); the fp32-parity FP16 split issues 3 '
-                         'MMAs per product and pads 100-column chunks to N=112 (issued_mma_*); equiv_hbm_* = bytes the '
-                         'unfused dp_tp_scatter would stream (SURVEY 8d) / this kernel\'s time')
+        out = dict(kernel=f'conv_fused_kernel<TpL3> ({dominant}: layer-3 ligand-ligand convolution)', bound='tensor')
+        out.update(dom)
+        out.update(traffic=traffic_bytes, peak_source=f'{peak_src} dense bf16 cuBLAS throughput (sustained)', all_layers=allk,
+                   note='achieved = algorithmic FLOPs E*(2*61*60 + 2*61*W + tp_flops) (both MLP layers + channel mixing) / CUDA-event '
+                        'time; the fp32-parity FP16 split issues 3 MMAs per product and pads 100-column chunks to N=112 '
+                        '(issued_mma_*); equiv_hbm_* = bytes the unfused dp_tp_scatter would stream (SURVEY 8d) / this '
+                        'kernel\'s time; traffic = dram__bytes_read.sum + dram__bytes_write.sum of this launch in '
+                        'profiles/ncu_conv_fused_r1_final.csv')
+        return out
 
     def roofline(self, peak_gbs, peak_src):
         """Aggregate over every dp_tp_scatter launch of the timed region (the kernel BASELINE.json's metric names)."""

@@ -108,6 +108,7 @@ def stamps(layer=3):
     t0 = int(d[0, 0, 0])
     ph = [int(x) - t0 for x in d[1, 50]] + [int(x) - t0 for x in d[1, 51]]
     print('phases (warp 0): prologue start %d, A ready %d, main loop end %d, staged %d, reduced %d, pair end %d' % tuple(ph))
+    print('epilogue (warp 0): after barrier 1 %d, rows staged %d, after barrier 2 %d' % tuple(int(x) - t0 for x in d[1, 52]))
     for i in range(22):
         m = [int(x) - t0 for x in d[0, i]]
         w0 = [int(x) - t0 for x in d[1, i]]
