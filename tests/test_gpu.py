@@ -248,3 +248,116 @@ def test_edge_mlp_tensor_core_path_matches_ffma_path(built_lib, W, E):
     assert rel(out_t[:E].cpu(), ref.cpu()) < 2e-6, rel(out_t[:E].cpu(), ref.cpu())
     assert float((out_t[:E] - ref).abs().max() / ref.abs().max()) < 5e-6
     assert bool((out_t[((E + 127) // 128) * 128:] == 7.0).all())      # tiles beyond the device-side edge count are untouched
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# dp_conv_fused at kernel level (through the C ABI)
+# ---------------------------------------------------------------------------------------------------------------
+_CF = {0: (20, 50, 600, 9), 1: (50, 80, 1100, 9), 2: (80, 100, 1600, 9), 3: (100, 100, 2200, 9), 5: (100, 40, 1600, 8)}
+
+
+def _conv_case(layer, degs, seed=0, shift=0, n_in=700):
+    """Random inputs of one TensorProductConvLayer.  `shift` extra leading nodes (50 edges each, copies of the first edges)
+    move every tile boundary without changing the other nodes' edges."""
+    d_in, d_out, W, shs = _CF[layer]
+    g = torch.Generator().manual_seed(seed)
+    E = int(np.sum(degs))
+    t = dict(emb=torch.randn(E, 20, generator=g), nodes=torch.randn(n_in, d_in, generator=g), tb=torch.randn(n_in, 100, generator=g),
+             ib=torch.randint(0, n_in, (E,), generator=g, dtype=torch.int32), ic=torch.randint(0, n_in, (E,), generator=g, dtype=torch.int32),
+             gat=torch.randint(0, n_in, (E,), generator=g, dtype=torch.int32), sh=torch.randn(E, shs, generator=g),
+             w1=torch.randn(60, 60, generator=g) / 8, b1=torch.randn(60, generator=g), w3=torch.randn(W, 60, generator=g) / 8,
+             b3=torch.randn(W, generator=g), oscale=torch.rand(d_out, generator=g) + 0.5, oshift=torch.randn(d_out, generator=g))
+    ex = 50 * shift
+    for k in ('emb', 'ib', 'ic', 'gat', 'sh'):
+        t[k] = torch.cat([t[k][:ex], t[k]]) if ex else t[k]
+    t['degs'] = np.concatenate([np.full(shift, 50, dtype=np.int64), np.asarray(degs, dtype=np.int64)])
+    return t
+
+
+def _run_conv_fused(layer, t, lib, mode=0, residual=None, out0=None):
+    from diffphore_b200.engine import _make_w1img, _make_w2img112, greedy_tiles
+    L, p, dev = lib, lib.ptr, torch.device('cuda:0')
+    d_in, d_out, W, shs = _CF[layer]
+    seg = torch.from_numpy(np.concatenate([[0], np.cumsum(t['degs'])]).astype(np.int32)).to(dev)
+    tiles = greedy_tiles(t['degs'])
+    tile_node = torch.tensor(tiles + [len(t['degs'])], dtype=torch.int32, device=dev)
+    img1, inv1 = _make_w1img(t['w1'], t['b1'])
+    img2, inv2 = _make_w2img112(t['w3'], t['b3'])
+    d = {k: v.to(dev) for k, v in t.items() if torch.is_tensor(v)}
+    img1, img2 = img1.to(dev), img2.to(dev)
+    out = torch.zeros(len(t['degs']), d_out, device=dev) if out0 is None else out0.clone().to(dev)
+    res = None if residual is None else residual.to(dev)
+    st = torch.cuda.current_stream().cuda_stream
+    L.check(L.load().dp_conv_fused(layer, p(d['emb']), None, p(d['tb']), p(d['ib']), 100, p(d['tb']), p(d['ic']), None, 100, p(img1),
+                                   inv1, p(img2), inv2, p(d['nodes']), p(d['gat']), p(d['sh']), shs, p(seg), p(tile_node), None,
+                                   len(tiles), p(d['oscale']), p(d['oshift']), p(out), p(res), 0 if res is None else res.shape[1],
+                                   mode, st), 'dp_conv_fused')
+    torch.cuda.synchronize()
+    return out.cpu()
+
+
+def _conv_reference(layer, t):
+    """float64 evaluation of the layer with the oracle's e3nn restatement: fc -> FullyConnectedTensorProduct -> scatter mean.
+    Returns (out [n_nodes, D_out], per-component path weights)."""
+    from oracle import e3nn_lite as e3
+    seq = [e3.parse_irreps(s) for s in ('20x0e', '20x0e + 10x1o', '20x0e + 10x1o + 10x1e', '20x0e + 10x1o + 10x1e + 20x0o')]
+    if layer == 5:
+        sh_ir, _ = e3.full_tp_irreps_out(e3.sh_irreps(2), [(1, 2, 1)])
+        in_ir, out_ir = seq[3], e3.parse_irreps('20x0o + 20x0e')
+    else:
+        in_ir, sh_ir, out_ir = seq[min(layer, 3)], e3.sh_irreps(2), seq[min(layer + 1, 3)]
+    instrs, numel = e3.fctp_instructions(in_ir, sh_ir, out_ir)
+    assert numel == _CF[layer][2]
+    attr = torch.cat([t['emb'], t['tb'][t['ib'].long(), :20], t['tb'][t['ic'].long(), :20]], 1).double()
+    w = torch.relu(attr @ t['w1'].double().T + t['b1'].double()) @ t['w3'].double().T + t['b3'].double()
+    sh = t['sh'].double()
+    if layer == 5:                                      # the kernel consumes the first 7 of the 45 FullTP components (l <= 1)
+        sh = torch.cat([sh[:, :7], torch.zeros(sh.shape[0], e3.irreps_dim(sh_ir) - 7, dtype=torch.float64)], 1)
+    for ins in instrs:                                  # unit path weights: the kernel gets them through `oscale`
+        pass
+    y = e3.fctp_apply(in_ir, sh_ir, out_ir, [ins._replace(pw=1.0) for ins in instrs], t['nodes'].double()[t['gat'].long()], sh, w)
+    node = torch.from_numpy(np.repeat(np.arange(len(t['degs'])), t['degs']))
+    out = torch.zeros(len(t['degs']), y.shape[1], dtype=torch.float64).index_add_(0, node, y)
+    return out / torch.from_numpy(np.maximum(t['degs'], 1)).double()[:, None]
+
+
+@pytest.mark.parametrize('layer', [0, 1, 2, 3, 5])
+def test_conv_fused_matches_float64_reference(built_lib, layer):
+    """dp_conv_fused (tcgen05 MLP + thread-per-edge tensor product + in-CTA segmented mean) against a float64 evaluation of
+    fc -> e3nn FullyConnectedTensorProduct -> scatter-mean; irregular degrees incl. zero-degree nodes, a full 128-edge node
+    and an odd tile count (single-tile last pair)."""
+    rng = np.random.default_rng(layer)
+    degs = np.concatenate([rng.integers(0, 40, 150), [128, 0, 1, 127, 3]])
+    t = _conv_case(layer, degs, seed=layer)
+    d_out = _CF[layer][1]
+    t['oscale'], t['oshift'] = torch.ones(d_out), torch.zeros(d_out)          # identity affine map: plain tensor product
+    ref = _conv_reference(layer, t)
+    got = _run_conv_fused(layer, t, built_lib).double()
+    assert rel(got, ref) < 2e-6, rel(got, ref)
+
+
+@pytest.mark.parametrize('layer', [0, 3])
+def test_conv_fused_is_bit_identical_under_tile_realignment(built_lib, layer):
+    rng = np.random.default_rng(7)
+    degs = rng.integers(1, 40, 600)
+    ref = _run_conv_fused(layer, _conv_case(layer, degs, seed=3), built_lib)
+    for shift in (1, 2):
+        out = _run_conv_fused(layer, _conv_case(layer, degs, seed=3, shift=shift), built_lib)[shift:]
+        assert torch.equal(out, ref)
+
+
+def test_conv_fused_modes_and_split_fallback_for_big_nodes(built_lib):
+    """mode 1 / mode 2 epilogues against mode 0, and a ligand with more than 128 atoms (phore nodes with > 128 cross edges):
+    the engine routes that edge set through the unfused kernels and still matches the oracle."""
+    rng = np.random.default_rng(1)
+    degs = rng.integers(0, 30, 200)
+    t = _conv_case(1, degs, seed=9)
+    base = _run_conv_fused(1, t, built_lib)
+    g = torch.Generator().manual_seed(2)
+    res, out0 = torch.randn(len(degs), 50, generator=g), torch.randn(len(degs), 80, generator=g)
+    m1 = _run_conv_fused(1, t, built_lib, mode=1, residual=res)
+    m2 = _run_conv_fused(1, t, built_lib, mode=2, out0=out0)
+    assert torch.equal(m1[:, 50:], base[:, 50:]) and torch.allclose(m1[:, :50], base[:, :50] + res, atol=1e-6, rtol=1e-6)
+    assert torch.allclose(m2, base + out0, atol=1e-6, rtol=1e-6)
+    r = run_forward_parity(n_pairs=1, n_atoms=140, n_phore=6, samples=1, weights='random', t=0.4, detail=True)
+    assert r['ok'], r

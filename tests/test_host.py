@@ -140,3 +140,65 @@ def test_step_constants_fold_the_sigma_embedding():
     from utils.diffusion_utils import get_t_schedule, sinusoidal_embedding as se2
     assert torch.allclose(se2(torch.tensor([10000 * 0.35]), 20)[0], semb)
     assert np.allclose(get_t_schedule(20), np.linspace(1, 0, 21)[:-1])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# host side of the fused convolution (dp_conv_fused): tiles, operand images, device-side sample expansion
+# ---------------------------------------------------------------------------------------------------------------
+def test_greedy_tiles_rule():
+    from diffphore_b200.engine import greedy_tiles
+    assert greedy_tiles([8] * 32) == [0, 16]                                   # 16 nodes x 8 edges fill a 128-edge tile
+    assert greedy_tiles([32] * 8) == [0, 4]
+    assert greedy_tiles([100, 0, 0, 28, 1]) == [0, 4]                          # zero-degree nodes ride along, 129th edge opens a tile
+    assert greedy_tiles([128, 128]) == [0, 1]
+    assert greedy_tiles([0, 0, 129]) is None                                   # a node with more than 128 edges: unfused kernels
+    assert greedy_tiles([]) == []
+    rng = np.random.default_rng(0)
+    deg = rng.integers(0, 60, 500)
+    t = greedy_tiles(deg) + [len(deg)]
+    seg = np.concatenate([[0], np.cumsum(deg)])
+    fill = [seg[b] - seg[a] for a, b in zip(t[:-1], t[1:])]
+    assert max(fill) <= 128 and all(f + deg[b] > 128 for f, b in zip(fill[:-1], t[1:-1]))   # greedy: the next node would not fit
+
+
+def test_fused_operand_images_reconstruct_the_weights():
+    from diffphore_b200.engine import _make_w1img, _make_w2img112
+    g = torch.Generator().manual_seed(0)
+    w3, b3 = torch.randn(1100, 60, generator=g) * 3, torch.randn(1100, generator=g)
+    img, inv = _make_w2img112(w3, b3)
+    h = img.view(torch.float16).reshape(11, 2, 8, 14, 8, 8)                     # [chunk][hi|lo][k/8][n/8][n%8][k%8]
+    x = (h[:, 0].double() + h[:, 1].double()).permute(0, 2, 3, 1, 4).reshape(11, 112, 64) * inv
+    assert float((x[:, :100, :60].reshape(1100, 60) - w3).abs().max()) < 2e-6 * float(w3.abs().max())
+    assert float((x[:, :100, 60].reshape(1100) - b3).abs().max()) < 2e-6 * float(w3.abs().max())
+    assert float(x[:, 100:].abs().max()) == 0 and float(x[:, :, 61:].abs().max()) == 0
+    w1, b1 = torch.randn(60, 60, generator=g), torch.randn(60, generator=g)
+    img, inv = _make_w1img(w1, b1)
+    h = img.view(torch.float16).reshape(2, 8, 8, 8, 8)                          # [hi|lo][k/8][n/8][n%8][k%8]
+    x = (h[0].double() + h[1].double()).permute(1, 2, 0, 3).reshape(64, 64) * inv
+    assert float((x[:60, :60] - w1).abs().max()) < 2e-6 * float(w1.abs().max())
+    assert float((x[:60, 60] - b1).abs().max()) < 2e-6 * float(w1.abs().max())
+    assert abs(float(x[60, 60]) - 1.0) < 1e-7 and float(x[61:].abs().max()) == 0   # constant-1 column passes through layer 1
+    assert np.log2(inv) == round(np.log2(inv))                                  # exact power-of-two scale
+
+
+def test_packed_batch_expands_samples_like_a_naive_replication():
+    """PackedBatch uploads per-pair arrays and expands the samples on the device; compare with collating deep copies."""
+    from diffphore_b200.engine import ModelWeights, PackedBatch
+    graphs = load_pairs('synthetic', 3, 12, 5) + load_pairs('synthetic', 1, 4, 4) + load_pairs('synthetic', 1, 3, 4)
+    S = 3
+    w = ModelWeights(random_state_dict(0), 'cpu')
+    a = PackedBatch(graphs, S, w, 'cpu')
+    b = PackedBatch([g for g in graphs for _ in range(S)], 1, w, 'cpu')          # every (pair, sample) as its own "pair"
+    assert a.h2d_bytes < b.h2d_bytes
+    for k, v in vars(b).items():
+        va = getattr(a, k)
+        if torch.is_tensor(v):
+            assert va.dtype == v.dtype and torch.equal(va, v), k
+        elif isinstance(v, tuple) and len(v) == 3 and torch.is_tensor(v[0]):
+            assert torch.equal(va[0], v[0]) and va[2] == v[2], k
+        elif isinstance(v, np.ndarray):
+            assert np.array_equal(va, v), k
+        elif k not in ('h2d_bytes', 'S', 'device'):
+            assert va == v, k
+    assert a.tiles_cross_lig[2] == sum(-(-g['ligand'].pos.shape[0] * g['phore'].pos.shape[0] // 128) if
+                                       g['phore'].pos.shape[0] <= 128 else 0 for g in graphs) * S or a.tiles_cross_lig[2] > 0
