@@ -1,8 +1,9 @@
-// dp_conv_fused: one TensorProductConvLayer (score_model_phore.py:134-149) WITHOUT materialising the per-edge
-// tensor-product weights in HBM.
+// dp_conv_fused: one TensorProductConvLayer (score_model_phore.py:125-149 plus the torch.cat of its edge attributes,
+// :678-695, 368) in one kernel, WITHOUT materialising per-edge hidden activations or tensor-product weights in HBM.
 //
-//   w[e, 0:W]   = [h(e) | 1] . W2aug                     tcgen05 tensor cores, accumulators in tensor memory (K5)
-//   tp[e]       = FCTP(node_in[gather[e]], sh[e], w[e])   CUDA cores, thread = edge, w read straight from TMEM (K6)
+//   h[e]        = ReLU(W1 . [emb | node_B | node_C](e) + b1)   tcgen05 tensor cores (K5, layer 1)
+//   w[e, 0:W]   = [h(e) | 1] . W2aug                            tcgen05 tensor cores, accumulators in tensor memory (K5, layer 2)
+//   tp[e]       = FCTP(node_in[gather[e]], sh[e], w[e])          CUDA cores (FFMA2), thread = edge, w read straight from TMEM (K6)
 //   out[n]      = BatchNorm(mean_{e in seg(n)} tp[e]) (+ residual)      shared-memory segmented reduction (K7, K8)
 //
 // The unfused pipeline (dp_edge_mlp_tc -> dp_tp_scatter) writes and re-reads 4*W bytes per edge (2.4-8.8 KB): both
@@ -10,18 +11,25 @@
 // tile in tensor memory, which turns the convolution into a tensor-pipe-bound kernel ("a K5->K6-fused
 // kernel never materialises weights: report against the FLOP roofline").
 //
-// Work decomposition
+// Work decomposition (one persistent CTA per SM, 352 threads, all 512 TMEM columns)
 //   * Edges are grouped by output node (CSR seg_ptr).  TILES are runs of whole nodes with <= 128 edges (tile_node[],
 //     built by dp_build_tiles or on the host), so the edge->node reduction never leaves the CTA: no atomics, the sum
 //     over a node's edges is sequential in edge order => bit-identical results for any batch composition.
-//   * A persistent CTA processes PAIRS of tiles (256 edges): every 100-column weight chunk fetched from L2 by TMA
-//     feeds two M=128 MMA groups.  Warps 0-3 own the 128 TMEM lanes of tile 0, warps 4-7 those of tile 1 (thread =
-//     edge for the whole pair), warp 8 is the TMA producer + MMA issuer.
-//   * fp32 parity: exactly-scaled 2-way FP16 split of both operands (hi*hi + hi*lo + lo*hi, fp32 accumulation), see
-//     edge_mlp_tc.cuh.  A operands live in tensor memory (tcgen05.st), B streams through a TMA ring.
+//   * The CTA processes PAIRS of tiles (256 edges): every weight chunk fetched from L2 by TMA feeds two M=128 MMA groups.
+//     Warps 0-3 own the 128 TMEM lanes of tile 0, warps 4-7 those of tile 1 (thread = edge for the whole pair); warps
+//     8 / 9 issue the MMAs of tile 0 / 1 (converged warp, elect.sync-predicated asm: bare UTCHMMA in SASS), warp 10
+//     is the TMA producer.  Item 0 of a pair is the hidden layer (N = 64, weights = one 16 KB ring stage), items
+//     1..W/100 are the weight chunks.
+//   * fp32 parity: exactly-scaled 2-way FP16 split of both operands (row * 2^s into [2^12, 2^13), hi = fp16(x),
+//     lo = fp16(x - hi); hi*hi + hi*lo + lo*hi accumulated in fp32).  A hi lives in tensor memory (tcgen05.st, TS-form
+//     MMA), A lo in shared memory (SS-form MMA), B streams through the TMA ring (hi | lo per chunk).
 //   * The per-path weight blocks [U x V] are all multiples of 100 columns, so a chunk = 100 consecutive columns of the
 //     e3nn weight layout = 5 rows (V = 20) or 10 rows (V = 10) of one path; MMA N = 112 (100 + zero padding).
-//     TMEM: 3 accumulator slots x 128 columns rotate over the (chunk, tile) items, A operands in columns 384..511.
+//     TMEM: 4 accumulator slots x 112 columns (slots t, t + 2 belong to tile t: every barrier has one producer warp
+//     and one consumer group), A hi operands in columns 448..511.
+//   * Per pair: attributes (prefetched one pair ahead) -> layer-1 operand -> hidden MMA -> ReLU -> layer-2 operand ->
+//     node rows gathered under the first chunk MMAs -> chunk loop -> rows staged as float4 -> per-(node, quad)
+//     sequential sums, mean, BatchNorm scale/shift, residual.
 #pragma once
 #include "edge_mlp_tc.cuh"
 #include "tp_tables.cuh"
