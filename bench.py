@@ -130,6 +130,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--pairs', type=int, default=N_PAIRS)
     ap.add_argument('--samples', type=int, default=SAMPLES)
+    ap.add_argument('--atoms', type=int, default=N_ATOMS, help='ligand atoms per synthetic pair (default: cfg2 = 32)')
+    ap.add_argument('--phore', type=int, default=N_PHORE, help='pharmacophore points per synthetic pair (default: cfg2 = 8)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     args = ap.parse_args()
@@ -175,7 +177,7 @@ def main():
     sd = random_state_dict(0)
     w = ModelWeights(sd, dev)
     sampler = DenoisingSampler(w, INF_STEPS)
-    graphs = make_pairs(args.pairs, N_ATOMS, N_PHORE, first=rank * args.pairs)
+    graphs = make_pairs(args.pairs, args.atoms, args.phore, first=rank * args.pairs)
     n_samples_local = args.pairs * args.samples
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
 
@@ -253,7 +255,10 @@ def main():
                           'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
                           'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
                           'data': 'synthetic graphs (diffphore_b200/synthetic.py), random-init weights of the shipped architecture',
-                          'config': {'workload': WORKLOAD, 'pairs_per_gpu': args.pairs, 'samples_per_pair': args.samples,
+                          'config': {'workload': WORKLOAD if (args.pairs, args.samples, args.atoms, args.phore) == (N_PAIRS, SAMPLES, N_ATOMS, N_PHORE)
+                                     else f'synthetic {args.pairs} pairs ({args.atoms} atoms / {args.phore} phore points) x {args.samples} samples x '
+                                          f'{INF_STEPS} denoising steps per GPU (NOT the headline configuration)',
+                                     'pairs_per_gpu': args.pairs, 'samples_per_pair': args.samples,
                                      'denoising_steps': INF_STEPS, 'l2': 'inputs larger than L2 (per conv: >= 130 MB of node features + 0.1-0.7 GB of per-edge hidden activations)',
                                      'parallelism': f'pairs sharded over {world} rank(s), one all_gather of poses'},
                           'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof,

@@ -657,7 +657,13 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
                         add[j] = 0.f;
                         if (it < items && d < Cfg::D_OUT) {
                             if (a.mode == 1) add[j] = (d < a.res_dim) ? __ldg(a.residual + (size_t)node * a.res_dim + d) : 0.0f;
-                            else if (a.mode == 2) add[j] = a.out[(size_t)node * Cfg::D_OUT + d];
+                            else if (a.mode == 2 && Cfg::D_OUT % 4 != 0) add[j] = a.out[(size_t)node * Cfg::D_OUT + d];
+                        }
+                    }
+                    if constexpr (Cfg::D_OUT % 4 == 0) {                     // 16-byte aligned output rows: one load per quad
+                        if (a.mode == 2 && it < items && 4 * q < Cfg::D_OUT) {        // (the last staged quad may be padding)
+                            const float4 t = *reinterpret_cast<const float4*>(a.out + (size_t)node * Cfg::D_OUT + 4 * q);
+                            add[0] = t.x; add[1] = t.y; add[2] = t.z; add[3] = t.w;
                         }
                     }
                 };
@@ -679,11 +685,19 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
                     const int deg = s1 - s0;
                     const float inv_deg = 1.0f / (float)(deg > 0 ? deg : 1);
                     const float sv[4] = {s.x, s.y, s.z, s.w};
+                    float ov[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int d = 4 * q + j;
-                        if (d < Cfg::D_OUT) orow[d] = sv[j] * inv_deg * osc[d] + osh[d] + add[j];
+                        ov[j] = d < Cfg::D_OUT ? sv[j] * inv_deg * osc[d] + osh[d] + add[j] : 0.f;
                         add[j] = add_n[j];
+                    }
+                    if constexpr (Cfg::D_OUT % 4 == 0) {
+                        if (4 * q < Cfg::D_OUT) *reinterpret_cast<float4*>(orow + 4 * q) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (4 * q + j < Cfg::D_OUT) orow[4 * q + j] = ov[j];
                     }
                 }
             }
