@@ -361,3 +361,21 @@ def test_conv_fused_modes_and_split_fallback_for_big_nodes(built_lib):
     assert torch.allclose(m2, base + out0, atol=1e-6, rtol=1e-6)
     r = run_forward_parity(n_pairs=1, n_atoms=140, n_phore=6, samples=1, weights='random', t=0.4, detail=True)
     assert r['ok'], r
+
+
+def test_cuda_graph_step_replay_is_bit_identical_to_eager_launches():
+    """Small chunks replay one captured step graph per denoising step (sampler._step_graph); poses must equal eager launches."""
+    from diffphore_b200.engine import ModelWeights
+    from diffphore_b200.sampler import DenoisingSampler
+    graphs = load_pairs('synthetic', 3, 20, 6)
+    sd = random_state_dict(7)
+    w = ModelWeights(sd, torch.device('cuda:0'))
+    init, noise, n_rot = make_draws(graphs, 2, 5, steps=4)
+    eager = DenoisingSampler(w, 4, cuda_graphs=False)
+    graph = DenoisingSampler(w, 4, cuda_graphs=True)
+    a, _ = eager.run(graphs, 2, noise=noise, init=init)
+    b, _ = graph.run(graphs, 2, noise=noise, init=init)
+    c, _ = graph.run(graphs, 2, noise=noise, init=init, no_random=True)
+    d, _ = eager.run(graphs, 2, noise=noise, init=init, no_random=True)
+    assert torch.equal(a, b) and torch.equal(c, d) and not torch.equal(a, c)
+    assert graph.gpu_launches == eager.gpu_launches
