@@ -132,6 +132,8 @@ def main():
     ap.add_argument('--samples', type=int, default=SAMPLES)
     ap.add_argument('--atoms', type=int, default=N_ATOMS, help='ligand atoms per synthetic pair (default: cfg2 = 32)')
     ap.add_argument('--phore', type=int, default=N_PHORE, help='pharmacophore points per synthetic pair (default: cfg2 = 8)')
+    ap.add_argument('--real', type=int, default=0, help='NOT the headline: the first N real-shaped pairs of tests/golden/real_pairs.npz '
+                                                        '(reference example ligands x the 79-node example pharmacophore), shipped checkpoint if present')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     args = ap.parse_args()
@@ -175,9 +177,14 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     sd = random_state_dict(0)
+    graphs = make_pairs(args.pairs, args.atoms, args.phore, first=rank * args.pairs)
+    if args.real:
+        from tests.parity_util import load_pairs, have_checkpoint, real_state_dict
+        graphs = load_pairs('real', args.real)
+        args.pairs = len(graphs)
+        sd = real_state_dict() if have_checkpoint() else sd
     w = ModelWeights(sd, dev)
     sampler = DenoisingSampler(w, INF_STEPS)
-    graphs = make_pairs(args.pairs, args.atoms, args.phore, first=rank * args.pairs)
     n_samples_local = args.pairs * args.samples
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
 
@@ -256,8 +263,10 @@ def main():
                           'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
                           'data': 'synthetic graphs (diffphore_b200/synthetic.py), random-init weights of the shipped architecture',
                           'config': {'workload': WORKLOAD if (args.pairs, args.samples, args.atoms, args.phore) == (N_PAIRS, SAMPLES, N_ATOMS, N_PHORE)
-                                     else f'synthetic {args.pairs} pairs ({args.atoms} atoms / {args.phore} phore points) x {args.samples} samples x '
-                                          f'{INF_STEPS} denoising steps per GPU (NOT the headline configuration)',
+                                     else (f'{args.pairs} real-shaped pairs (reference example ligands x 79-node pharmacophore) x {args.samples} samples x '
+                                           f'{INF_STEPS} steps (NOT the headline configuration)' if args.real else
+                                           f'synthetic {args.pairs} pairs ({args.atoms} atoms / {args.phore} phore points) x {args.samples} samples x '
+                                           f'{INF_STEPS} denoising steps per GPU (NOT the headline configuration)'),
                                      'pairs_per_gpu': args.pairs, 'samples_per_pair': args.samples,
                                      'denoising_steps': INF_STEPS, 'l2': 'inputs larger than L2 (per conv: >= 130 MB of node features + 0.1-0.7 GB of per-edge hidden activations)',
                                      'parallelism': f'pairs sharded over {world} rank(s), one all_gather of poses'},
