@@ -83,7 +83,12 @@ struct ConvFusedArgs {
 
 template <class Cfg>
 struct ConvFusedSmem {
-    static constexpr int XS = Cfg::D_IN | 1;                              // odd row strides: conflict-free thread-per-row access
+    // Gathered node rows: stride = D_IN rounded so that rows stay 16-byte (8-byte for D_IN = 50) aligned for one vector store per
+    // lane, with an odd number of vectors per row: the thread-per-row scalar reads of the main loop are then at most 4-way bank
+    // conflicted (a few hundred LDS per pair on an otherwise idle LSU), while the gather needs 4x fewer store instructions
+    // than an odd scalar stride (measured: the gather, not the reads, was exposed).
+    static constexpr int XVEC = (Cfg::D_IN % 4 == 0) ? 4 : 2;
+    static constexpr int XS = (((Cfg::D_IN / XVEC) | 1)) * XVEC;
     static constexpr int OQ = ((Cfg::D_OUT + 3) / 4) | 1;                // float4 per staged row, odd: conflict-free STS.128 / LDS.128
     static constexpr int OS = 4 * OQ;
     static constexpr int ROW_FLOATS = XS > OS ? XS : OS;
@@ -587,9 +592,8 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
             // ---- prologue 4 (under the first chunk's MMAs): gathered node rows -> smem, warp-cooperative (lanes walk a row:
             //      coalesced in global memory, conflict-free in the odd-stride smem rows), 32 rows = 4 x 32 loads in flight ----
             if (active) {
-                // lanes read VEC consecutive floats of a row (one 16- or 8-byte load per row and lane) and write them to the
-                // odd-stride smem row in a lane-rotated order, so that every scalar store instruction is bank-conflict free
-                constexpr int VEC = (Cfg::D_IN % 4 == 0) ? 4 : 2;
+                // lanes read VEC consecutive floats of a row: one 16- or 8-byte load and one vector store per row and lane
+                constexpr int VEC = S::XVEC;
                 constexpr int NL = Cfg::D_IN / VEC;                         // active lanes per row (<= 32)
                 static_assert(Cfg::D_IN % VEC == 0 && NL <= 32, "row gather layout");
                 float v[32][VEC];
@@ -610,19 +614,12 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
                         for (int i = 0; i < VEC; ++i) v[j][i] = 0.f;
                     }
                 }
-                const int rot = lane * VEC / 32;                            // lanes L and L + 32 / VEC would hit the same bank
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     float* dst = xs + (size_t)(tid - lane + j) * S::XS + VEC * lane;
                     if (lane < NL) {
-#pragma unroll
-                        for (int i = 0; i < VEC; ++i) {
-                            const int k = (i + rot) & (VEC - 1);
-                            float val = v[j][0];
-#pragma unroll
-                            for (int q = 1; q < VEC; ++q) val = (k == q) ? v[j][q] : val;
-                            dst[k] = val;
-                        }
+                        if constexpr (VEC == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+                        else *reinterpret_cast<float2*>(dst) = make_float2(v[j][0], v[j][1]);
                     }
                 }
             }
@@ -667,37 +664,44 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
                         }
                     }
                 };
-                float add[4], add_n[4];
-                load_add(tid, add);
-                for (int it = tid; it < items; it += CF_WORKERS) {
-                    load_add(it + CF_WORKERS, add_n);
-                    const int nl = it / S::OQ, q = it % S::OQ, node = ix.n_lo + nl;
-                    const int s0 = node_seg[nl], s1 = node_seg[nl + 1];
-                    float* orow = a.out + (size_t)node * Cfg::D_OUT;
-                    const int r0 = node < ix.n_mid ? s0 - e_lo : 128 + s0 - e_mid;
-                    const float* sp = stg + (size_t)r0 * S::OS + 4 * q;
-                    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+                // Batches of 4 items per thread: their residual / running-sum loads are all in flight before the first sum is
+                // consumed (one exposed HBM round trip per batch; a one-ahead prefetch still exposed one per item).
+#pragma unroll 1
+                for (int it0 = tid; it0 < items; it0 += 4 * CF_WORKERS) {
+                    float add[4][4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) load_add(it0 + u * CF_WORKERS, add[u]);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int it = it0 + u * CF_WORKERS;
+                        if (it >= items) break;
+                        const int nl = it / S::OQ, q = it % S::OQ, node = ix.n_lo + nl;
+                        const int s0 = node_seg[nl], s1 = node_seg[nl + 1];
+                        float* orow = a.out + (size_t)node * Cfg::D_OUT;
+                        const int r0 = node < ix.n_mid ? s0 - e_lo : 128 + s0 - e_mid;
+                        const float* sp = stg + (size_t)r0 * S::OS + 4 * q;
+                        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-                    for (int r = 0; r < s1 - s0; ++r) {                      // sequential in edge order: composition-invariant
-                        const float4 v = *reinterpret_cast<const float4*>(sp + (size_t)r * S::OS);
-                        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-                    }
-                    const int deg = s1 - s0;
-                    const float inv_deg = 1.0f / (float)(deg > 0 ? deg : 1);
-                    const float sv[4] = {s.x, s.y, s.z, s.w};
-                    float ov[4];
+                        for (int r = 0; r < s1 - s0; ++r) {                  // sequential in edge order: composition-invariant
+                            const float4 v = *reinterpret_cast<const float4*>(sp + (size_t)r * S::OS);
+                            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                        }
+                        const int deg = s1 - s0;
+                        const float inv_deg = 1.0f / (float)(deg > 0 ? deg : 1);
+                        const float sv[4] = {s.x, s.y, s.z, s.w};
+                        float ov[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int d = 4 * q + j;
-                        ov[j] = d < Cfg::D_OUT ? sv[j] * inv_deg * osc[d] + osh[d] + add[j] : 0.f;
-                        add[j] = add_n[j];
-                    }
-                    if constexpr (Cfg::D_OUT % 4 == 0) {
-                        if (4 * q < Cfg::D_OUT) *reinterpret_cast<float4*>(orow + 4 * q) = make_float4(ov[0], ov[1], ov[2], ov[3]);
-                    } else {
+                        for (int j = 0; j < 4; ++j) {
+                            const int d = 4 * q + j;
+                            ov[j] = d < Cfg::D_OUT ? sv[j] * inv_deg * osc[d] + osh[d] + add[u][j] : 0.f;
+                        }
+                        if constexpr (Cfg::D_OUT % 4 == 0) {
+                            if (4 * q < Cfg::D_OUT) *reinterpret_cast<float4*>(orow + 4 * q) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (4 * q + j < Cfg::D_OUT) orow[4 * q + j] = ov[j];
+                            for (int j = 0; j < 4; ++j)
+                                if (4 * q + j < Cfg::D_OUT) orow[4 * q + j] = ov[j];
+                        }
                     }
                 }
             }
