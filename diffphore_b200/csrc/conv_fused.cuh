@@ -249,11 +249,11 @@ __device__ __forceinline__ void cf_chunk(uint32_t tslot, const float* __restrict
     }
 }
 
-template <class Cfg, int P, bool PROBE>
+template <class Cfg, int P, int END, bool PROBE>
 __device__ __forceinline__ void cf_paths(uint32_t tmem_lane_base, uint64_t* t_full, uint64_t* t_empty, uint32_t& item, int tile,
                                          int ntile, bool active, const float* __restrict__ xrow, const float* shv,
                                          float2 (&acc)[Cfg::D_OUT / 2], int lane, bool probe_on, uint32_t item0, long long* a_dbg) {
-    if constexpr (P < Cfg::NP) {
+    if constexpr (P < END) {
         constexpr TpPath p = Cfg::paths[P];
         constexpr int V = Cfg::outs[p.oi].V;
         constexpr int NCH = p.U * V / CF_CHUNK, R = CF_CHUNK / V;
@@ -276,7 +276,7 @@ __device__ __forceinline__ void cf_paths(uint32_t tmem_lane_base, uint64_t* t_fu
             }
             if (active) ++item;
         }
-        cf_paths<Cfg, P + 1, PROBE>(tmem_lane_base, t_full, t_empty, item, tile, ntile, active, xrow, shv, acc, lane, probe_on, item0, a_dbg);
+        cf_paths<Cfg, P + 1, END, PROBE>(tmem_lane_base, t_full, t_empty, item, tile, ntile, active, xrow, shv, acc, lane, probe_on, item0, a_dbg);
     }
 }
 
@@ -554,13 +554,10 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
             __syncwarp();
             if (lane == 0) tc_mbar_arrive(&a_ready[0]);                    // layer-1 operands in place
             CF_STAMP(1, 50, 1);
-            // ---- prologue 2 (under the hidden-layer MMA): seg_ptr of the pair's nodes -> smem for the epilogue, SH -> registers,
-            //      indices of the next pair (their round trips hide behind this pair) ----
+            // ---- prologue 2 (under the hidden-layer MMA): seg_ptr of the pair's nodes -> smem for the epilogue, SH -> registers ----
             for (int i = tid; i <= ix.n_hi - ix.n_lo; i += CF_WORKERS) node_seg[i] = a.seg_ptr[ix.n_lo + i];
 #pragma unroll
             for (int i = 0; i < Cfg::SH_USED; ++i) shv[i] = (active && valid) ? __ldg(a.sh + (size_t)ix.ce * a.sh_stride + i) : 0.f;
-            Idx nx = ix;
-            if (pi + 1 < my_pairs) nx = fetch(pair + (int)gridDim.x);
             // ---- prologue 3: hidden activations h = ReLU(D1) from tensor memory -> layer-2 A operand ----
             float rs = 0.f;
             if (active) {
@@ -628,7 +625,13 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
             float2 acc[Cfg::D_OUT / 2];
 #pragma unroll
             for (int d = 0; d < Cfg::D_OUT / 2; ++d) acc[d] = make_float2(0.f, 0.f);
-            cf_paths<Cfg, 0, PROBE>(lane_base, t_full, t_empty, item, tile, ntile, active, xrow, shv, acc, lane, pi == 1, item, a_dbg);
+            // The next pair's indices are a chain of three dependent global loads (tile -> segment -> edge level).  Inside the
+            // chunk loop its stalls are free: the workers drain a chunk in about half the time the tensor pipe needs for it.
+            const uint32_t item0 = item;
+            cf_paths<Cfg, 0, 1, PROBE>(lane_base, t_full, t_empty, item, tile, ntile, active, xrow, shv, acc, lane, pi == 1, item0, a_dbg);
+            Idx nx = ix;
+            if (pi + 1 < my_pairs) nx = fetch(pair + (int)gridDim.x);
+            cf_paths<Cfg, 1, Cfg::NP, PROBE>(lane_base, t_full, t_empty, item, tile, ntile, active, xrow, shv, acc, lane, pi == 1, item0, a_dbg);
             CF_STAMP(1, 50, 2);
             // ---- epilogue: per-edge results -> smem (aliases the node rows), segmented mean + BatchNorm + residual ----
             cf_bar_workers();                                              // every worker is done with its node row
