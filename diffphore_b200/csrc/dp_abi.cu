@@ -186,7 +186,7 @@ int dp_debug_edge_hidden(const float* emb, const float* tb, const int32_t* idxB,
     a.emb = emb; a.perm = nullptr; a.tb = tb; a.idxB = idxB; a.strideB = strideB; a.tc = tc; a.idxC = idxC; a.idxC2 = nullptr;
     a.strideC = strideC; a.w1 = w1; a.b1 = b1; a.w2t = nullptr; a.in_dim = 60; a.hid = 60; a.W = 0;
     a.n_edges_dev = nullptr; a.n_edges = n_edges; a.out = nullptr;
-    edge_hidden_kernel<<<min((n_edges + EH_TILE - 1) / EH_TILE, 148 * 6), EH_THREADS, 0, ST(stream)>>>(a, h_scratch, 0);
+    edge_hidden_kernel<<<min((n_edges + EH_TILE - 1) / EH_TILE, 148 * 6), EH_THREADS, 0, ST(stream)>>>(a, h_scratch);
     return dp_check_launch("edge_hidden");
 }
 

@@ -108,7 +108,7 @@ __device__ long long* g_tc_dbg = nullptr;     // profiling aid: per-phase clock6
 #define EH_THREADS 128
 #define EH_TILE 64                  // edges per CTA iteration
 #define EH_LD 68                    // padded row length of the transposed attribute tile
-__global__ void __launch_bounds__(EH_THREADS, 6) edge_hidden_kernel(EdgeMlpArgs a, float* __restrict__ himg, int interleave) {
+__global__ void __launch_bounds__(EH_THREADS, 6) edge_hidden_kernel(EdgeMlpArgs a, float* __restrict__ himg) {
     // register-tiled SGEMM  h[64 edges, 64] = attr[64, 60] . W1T[60, 64]: a thread owns 4 edges x 8 outputs, per k it
     // reads 4 attributes (one float4 of the k-major tile) and 8 weights (two broadcast float4) for 32 FMAs.  Small tiles
     // (32 KB of shared memory, <= 80 registers) keep 6-7 CTAs resident per SM so that the two dependent gather round
@@ -181,12 +181,9 @@ __global__ void __launch_bounds__(EH_THREADS, 6) edge_hidden_kernel(EdgeMlpArgs 
                 const int o = o0 + j;
                 r[j] = o < 60 ? fmaxf(h[i][j], 0.f) : (o == 60 ? 1.0f : 0.f);
             }
-            const size_t e = (size_t)e0 + m0 + i;
-            // row-major [edge][64] for dp_edge_mlp_tc; edge-interleaved [e / 32][16 quads][e % 32][4] for dp_conv_fused, whose
-            // thread-per-edge quad loads then coalesce across a warp
-            float* dst = interleave ? himg + ((e >> 5) * 16 + (o0 >> 2)) * 128 + (e & 31) * 4 : himg + e * TC_K + o0;
+            float* dst = himg + ((size_t)e0 + m0 + i) * TC_K + o0;
             *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
-            *reinterpret_cast<float4*>(dst + (interleave ? 128 : 4)) = make_float4(r[4], r[5], r[6], r[7]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(r[4], r[5], r[6], r[7]);
         }
     }
 }
@@ -452,7 +449,7 @@ static int edge_mlp_tc_launch(const EdgeMlpTcArgs& t, cudaStream_t st) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     }
-    edge_hidden_kernel<<<dim3(min((a.n_edges + EH_TILE - 1) / EH_TILE, n_sm * 6)), EH_THREADS, 0, st>>>(a, t.himg, 0);
+    edge_hidden_kernel<<<dim3(min((a.n_edges + EH_TILE - 1) / EH_TILE, n_sm * 6)), EH_THREADS, 0, st>>>(a, t.himg);
     edge_mlp_tc_kernel<<<dim3((a.n_edges + 255) / 256), TC_THREADS, TC2_SMEM_BYTES, st>>>(t, map);
     return dp_check_launch("edge_mlp_tc");
 }
