@@ -379,3 +379,29 @@ def test_cuda_graph_step_replay_is_bit_identical_to_eager_launches():
     d, _ = eager.run(graphs, 2, noise=noise, init=init, no_random=True)
     assert torch.equal(a, b) and torch.equal(c, d) and not torch.equal(a, c)
     assert graph.gpu_launches == eager.gpu_launches
+
+
+@pytest.mark.parametrize('n_pairs,n_atoms,n_phore,S', [(48, 64, 12, 8), (1, 128, 16, 40)])
+def test_size_independent_properties_cfg4_cfg5_shapes(n_pairs, n_atoms, n_phore, S):
+    """BASELINE cfg4 / cfg5 shapes (too big for the oracle at full sample counts): identical draws for all samples of a pair
+    => bit-identical poses within the pair; bond lengths preserved by the rigid + torsion updates; everything finite."""
+    from diffphore_b200.engine import ModelWeights
+    from diffphore_b200.sampler import DenoisingSampler
+    from diffphore_b200.synthetic import make_pairs
+    steps = 3
+    graphs = make_pairs(n_pairs, n_atoms, n_phore)
+    smp = DenoisingSampler(ModelWeights(random_state_dict(0), torch.device('cuda:0')), steps)
+    init1, noise1, n_rot1 = make_draws(graphs, 1, 3, steps=steps)
+    offs = np.concatenate([[0], np.cumsum(n_rot1)])
+    rep_g = lambda a: np.repeat(a, S, axis=0)
+    rep_r = lambda a: np.concatenate([np.tile(a[offs[i]:offs[i + 1]], S) for i in range(n_pairs)])
+    init = dict(tor=rep_r(init1['tor']), rot=rep_g(init1['rot']), tr=rep_g(init1['tr']))
+    noise = [dict(tr=rep_g(z['tr']), rot=rep_g(z['rot']), tor=rep_r(z['tor'])) for z in noise1]
+    pos, ptr = smp.run(graphs, S, noise=noise, init=init)
+    assert torch.isfinite(pos).all()
+    pos = pos.reshape(n_pairs, S, n_atoms, 3)
+    assert torch.equal(pos, pos[:, :1].expand_as(pos))
+    for p in (0, n_pairs - 1):
+        ei = graphs[p]['ligand', 'ligand'].edge_index
+        d = (pos[p, 0][ei[0]] - pos[p, 0][ei[1]]).norm(dim=1)
+        assert torch.allclose(d, torch.full_like(d, 1.5), atol=5e-4)
