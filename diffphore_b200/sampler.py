@@ -169,7 +169,7 @@ class DenoisingSampler:
                     ws.sc_buf.copy_(sc)
                     if z[0] is not None:
                         for dst, src in zip(ws.z_buf, z):
-                            dst.copy_(src)
+                            dst[:src.shape[0]].copy_(src)       # (the torsion buffer keeps one slot when n_rot = 0)
                     graph.replay()
                     ws.n_launches += n_l
                     continue

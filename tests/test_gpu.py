@@ -405,3 +405,18 @@ def test_size_independent_properties_cfg4_cfg5_shapes(n_pairs, n_atoms, n_phore,
         ei = graphs[p]['ligand', 'ligand'].edge_index
         d = (pos[p, 0][ei[0]] - pos[p, 0][ei[1]]).norm(dim=1)
         assert torch.allclose(d, torch.full_like(d, 1.5), atol=5e-4)
+
+
+def test_sampler_handles_ligands_without_rotatable_bonds_and_single_graph_jobs():
+    """n_rot = 0 (tor_pred empty, smp:354-358) and a one-graph job through the public sampler (CUDA-graph replay and eager)."""
+    from diffphore_b200.engine import ModelWeights
+    from diffphore_b200.sampler import DenoisingSampler
+    w = ModelWeights(random_state_dict(3), torch.device('cuda:0'))
+    g3 = load_pairs('synthetic', 1, 3, 4)
+    assert int(g3[0]['ligand'].edge_mask.sum()) == 0
+    mixed = g3 + load_pairs('synthetic', 2, 10, 5)
+    for graphs, S in ((g3, 1), (g3, 3), (mixed, 2)):
+        init, noise, n_rot = make_draws(graphs, S, 1, steps=3)
+        a, _ = DenoisingSampler(w, 3, cuda_graphs=True).run(graphs, S, noise=noise, init=init)
+        b, _ = DenoisingSampler(w, 3, cuda_graphs=False).run(graphs, S, noise=noise, init=init)
+        assert torch.isfinite(a).all() and torch.equal(a, b)
