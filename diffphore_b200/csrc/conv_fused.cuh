@@ -529,12 +529,13 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
                 const int ex = (int)((__float_as_uint(m) >> 23) & 0xFF) - 127;
                 const float sc = __uint_as_float((uint32_t)(127 + 12 - ex) << 23);
                 uint32_t hi_p[32], lo_p[32];
+                const float2 sc2 = make_float2(sc, sc), neg1 = make_float2(-1.f, -1.f);
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
-                    const float x0 = v[2 * c] * sc, x1 = v[2 * c + 1] * sc;
-                    const __half2 hh = __floats2half2_rn(x0, x1);           // packed conversions (F2FP), 2 values per instruction
-                    const float2 hf = __half22float2(hh);
-                    const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                    const float2 x = __fmul2_rn(make_float2(v[2 * c], v[2 * c + 1]), sc2);    // packed fp32 ops (sm_100)
+                    const __half2 hh = __floats2half2_rn(x.x, x.y);         // packed conversions (F2FP), 2 values per instruction
+                    const float2 lo = __ffma2_rn(__half22float2(hh), neg1, x);                  // x - hi, exact
+                    const __half2 ll = __floats2half2_rn(lo.x, lo.y);
                     hi_p[c] = *reinterpret_cast<const uint32_t*>(&hh);
                     lo_p[c] = *reinterpret_cast<const uint32_t*>(&ll);
                 }
