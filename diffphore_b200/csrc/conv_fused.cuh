@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
         // other's waits.  Each (slot, barrier) pair has exactly one producer and one consumer group, so every parity wait
         // stays within one phase of its barrier. =================
         {
-            const int t = warp - 8;
+            const int t = __reduce_max_sync(0xffffffffu, warp - 8);         // warp-uniform by construction: keep it in a uniform register
             // instruction descriptor: D = F32, A = B = F16, K-major, N = 112, M = 128
             const uint32_t idesc = (1u << 4) | ((uint32_t)(CF_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t b_base = tc_smem(b_st);
