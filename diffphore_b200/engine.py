@@ -240,9 +240,10 @@ class ModelWeights:
         tt = torch.tensor(t, dtype=torch.float32)
         return tuple(float((c[f'{k}_sigma_min'] ** (1 - tt) * c[f'{k}_sigma_max'] ** tt).item()) for k in ('tr', 'rot', 'tor'))
 
-    def step_consts(self, t, so3_norm, torus_norm, dt=None):
+    def step_consts(self, t, so3_norm, torus_norm, dt=None, ode=False):
         """256-float block for noise level t.  so3_norm / torus_norm: callables sigma(np.float32 array) -> array
-        (utils/so3.py:92-96, utils/torus.py:82-86).  dt: Euler–Maruyama step (None -> score model only)."""
+        (utils/so3.py:92-96, utils/torus.py:82-86).  dt: Euler–Maruyama step (None -> score model only).
+        ode: probability-flow update 0.5 g^2 dt score without noise (sampling.py:226-228,240-241)."""
         c, h = self.cfg, self.h
         semb = sinusoidal_embedding(float(t), c['sigma_embed_dim'], c['embedding_scale'])
         out = torch.zeros(L.SC['SIZE'], dtype=torch.float32)
@@ -275,6 +276,9 @@ class ModelWeights:
             out[183], out[184] = tr_g ** 2 * dt, tr_g * math.sqrt(dt)
             out[185], out[186] = rot_g ** 2 * dt, rot_g * math.sqrt(dt)
             out[187], out[188] = tor_g ** 2 * dt, tor_g * math.sqrt(dt)
+            if ode:
+                out[183], out[185], out[187] = 0.5 * tr_g ** 2 * dt, 0.5 * rot_g ** 2 * dt, 0.5 * tor_g ** 2 * dt
+                out[184] = out[186] = out[188] = 0.0
         return out
 
 

@@ -31,7 +31,7 @@ def random_rotations(n, generator=None, device='cpu'):
 class DenoisingSampler:
     def __init__(self, weights: ModelWeights, inference_steps=20, so3_norm=None, torus_norm=None,
                  weight_buffer_bytes=24 << 30, no_final_step_noise=False, resident_bytes=48 << 30,
-                 cuda_graphs=True, graph_max_graphs=2048):
+                 cuda_graphs=True, graph_max_graphs=2048, ode=False):
         self.w = weights
         self.engine = Engine(weights)
         self.steps = inference_steps
@@ -42,11 +42,12 @@ class DenoisingSampler:
         # small chunks are launch-bound: replay one captured step graph per denoising step (see _step_graph)
         self.cuda_graphs, self.graph_max_graphs = cuda_graphs, graph_max_graphs
         self.no_final_step_noise = no_final_step_noise
+        self.ode = ode                                   # --ode: 0.5 g^2 dt score, no noise (sampling.py:226-228)
         sched = get_t_schedule(inference_steps)
         rows = []
         for k in range(inference_steps):
             dt = sched[k] - sched[k + 1] if k < inference_steps - 1 else sched[k]          # sampling.py:206-208
-            rows.append(weights.step_consts(float(sched[k]), self.so3, self.torus, dt=float(dt)))
+            rows.append(weights.step_consts(float(sched[k]), self.so3, self.torus, dt=float(dt), ode=ode))
         self.sched = sched
         self.consts = torch.stack(rows).to(weights.device)                                 # [steps, 256]
         self.gpu_launches = 0
@@ -143,8 +144,11 @@ class DenoisingSampler:
         b.pos.copy_(pos0); b.norm.copy_(norm0)         # (capture does not execute, but keep the pose exactly as it was)
         return cache[key]
 
-    def run_resident(self, resident, noise=None, no_random=False, generator=None, trace=None, no_torsion=False, timer=None):
-        """The 20-step loop (sampling.py:204-255) over device-resident chunks; poses end up in each chunk's b.pos."""
+    def run_resident(self, resident, noise=None, no_random=False, generator=None, trace=None, no_torsion=False, timer=None,
+                     pose_trace=None):
+        """The 20-step loop (sampling.py:204-255) over device-resident chunks; poses end up in each chunk's b.pos.
+        pose_trace: optional list; receives per chunk a device tensor [steps + 1, n_lig, 3] = the initial pose and the pose
+        after every step (`keep_update`: initial_poses / docked_poses of inference.py:191-192, diffusion_utils.py:71-77)."""
         dev = self.w.device
         self.engine.timer = timer
         g_off = r_off = 0
@@ -152,10 +156,11 @@ class DenoisingSampler:
             n0 = ws.n_launches
             sl_g, sl_r = slice(g_off, g_off + b.B), slice(r_off, r_off + b.n_rot)
             use_graph = self.cuda_graphs and timer is None and trace is None and b.B <= self.graph_max_graphs
+            traj = [b.pos.clone()] if pose_trace is not None else None
             for k in range(self.steps):
                 sc = self.consts[k]
                 last = k == self.steps - 1
-                if no_random or (self.no_final_step_noise and last):
+                if no_random or self.ode or (self.no_final_step_noise and last):
                     z = (None, None, None)
                 elif noise is None:
                     z = (torch.randn(b.B, 3, generator=generator, device=dev),
@@ -172,11 +177,17 @@ class DenoisingSampler:
                             dst[:src.shape[0]].copy_(src)       # (the torsion buffer keeps one slot when n_rot = 0)
                     graph.replay()
                     ws.n_launches += n_l
+                    if traj is not None:
+                        traj.append(b.pos.clone())
                     continue
                 self.engine.forward(b, ws, sc)
                 if trace is not None:
                     trace.append((ws.tr.clone().cpu(), ws.rot.clone().cpu(), ws.tor[:b.n_rot].clone().cpu()))
                 self.engine.update(b, ws, sc, *z, no_torsion=no_torsion)
+                if traj is not None:
+                    traj.append(b.pos.clone())
+            if traj is not None:
+                pose_trace.append(torch.stack(traj))
             self.gpu_launches += ws.n_launches - n0
             g_off += b.B
             r_off += b.n_rot
@@ -184,15 +195,19 @@ class DenoisingSampler:
 
     # ------------------------------------------------------------------ host-facing API
     def run(self, graphs, samples_per_graph=1, noise=None, init=None, no_random=False, generator=None,
-            randomize=True, trace=None, no_torsion=False, pinned=False):
+            randomize=True, trace=None, no_torsion=False, pinned=False, keep_update=False):
         """Denoise `samples_per_graph` poses for every pair in `graphs` (host graphs in, host poses out).
 
         init : None (device RNG) or dict(tor=[sum n_rot] , rot=[B,3,3], tr=[B,3]) in graph order (pair-major).
         noise: None (device RNG, or zeros when no_random) or list over steps of dict(tr=[B,3], rot=[B,3], tor=[n_rot]).
+        keep_update: also keep the pose after every step; `self.last_trajectory` = CPU tensor [steps + 1, n_lig_total, 3].
         Returns (pos [n_lig_total,3] float32 CPU tensor, lig_ptr numpy [B+1])."""
         resident = self.prepare(graphs, samples_per_graph)
         self.reset(resident, generator=generator, init=init, randomize=randomize, no_torsion=no_torsion)
-        self.run_resident(resident, noise=noise, no_random=no_random, generator=generator, trace=trace, no_torsion=no_torsion)
+        pose_trace = [] if keep_update else None
+        self.run_resident(resident, noise=noise, no_random=no_random, generator=generator, trace=trace, no_torsion=no_torsion,
+                          pose_trace=pose_trace)
+        self.last_trajectory = torch.cat(pose_trace, dim=1).cpu() if keep_update else None
         n_tot = sum(b.n_lig for b, _, _, _ in resident)
         out = torch.empty(n_tot, 3, dtype=torch.float32, pin_memory=pinned)
         ptr, o = [0], 0

@@ -144,8 +144,8 @@ def set_time(batch, t, b):
 
 
 def sampling(data_list, model, inference_steps, cfg, collate, batch_size, noise=None, no_torsion=False,
-             trace=None):
-    """sampling_phore (sampling.py:174-255), Euler–Maruyama branch (ode=False).
+             trace=None, ode=False):
+    """sampling_phore (sampling.py:174-255): Euler–Maruyama, or the probability-flow ODE branch (:226-228,240-241).
 
     noise: None (-> no_random=True, zeros) or a list over steps of dicts
            {'tr': [n,3], 'rot': [n,3], 'tor': [sum n_rot]} in data_list order.
@@ -176,11 +176,16 @@ def sampling(data_list, model, inference_steps, cfg, collate, batch_size, noise=
                 tr_z = torch.as_tensor(noise[t_idx]['tr'][g0:g0 + b], dtype=torch.float32)
                 rot_z = torch.as_tensor(noise[t_idx]['rot'][g0:g0 + b], dtype=torch.float32)
                 tor_z = torch.as_tensor(noise[t_idx]['tor'][tor0:tor0 + n_tor], dtype=torch.float32)
-            tr_perturb = (tr_g ** 2 * dt * tr_score + tr_g * np.sqrt(dt) * tr_z)
-            rot_perturb = (rot_score * dt * rot_g ** 2 + rot_g * np.sqrt(dt) * rot_z)
+            if ode:
+                tr_perturb = 0.5 * tr_g ** 2 * dt * tr_score
+                rot_perturb = 0.5 * rot_score * dt * rot_g ** 2
+            else:
+                tr_perturb = (tr_g ** 2 * dt * tr_score + tr_g * np.sqrt(dt) * tr_z)
+                rot_perturb = (rot_score * dt * rot_g ** 2 + rot_g * np.sqrt(dt) * rot_z)
             if not no_torsion:
                 tor_g = tor_sigma * torch.sqrt(torch.tensor(2 * np.log(cfg['tor_sigma_max'] / cfg['tor_sigma_min'])))
-                tor_perturb = (tor_g ** 2 * dt * tor_score + tor_g * np.sqrt(dt) * tor_z).numpy()
+                tor_perturb = (0.5 * tor_g ** 2 * dt * tor_score).numpy() if ode else \
+                    (tor_g ** 2 * dt * tor_score + tor_g * np.sqrt(dt) * tor_z).numpy()
             graphs = batch.to_data_list()
             off = 0
             for i, g in enumerate(graphs):

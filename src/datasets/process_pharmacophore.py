@@ -1,7 +1,7 @@
 """Pharmacophore (.phore) ingestion and the AncPhore scoring hand-off, host side.
 
 Mirrors /root/reference/src/datasets/process_pharmacophore.py: `parse_phore` (:78-152), `parse_phore_line`
-(:751-789), `get_phore_graph` (:634-714), `phore_featurizer` (:717-748), `parse_score_file` (:885),
+(:751-789), `get_phore_graph` (:634-714), `phore_featurizer` (:717-748), `parse_score_file` (:885-925),
 `calc_phore_fitting` (:930-1000).  Pure Python / numpy — no RDKit needed for this half of the preprocessing.
 """
 import os
@@ -94,38 +94,59 @@ def get_phore_graph(phore, graph, consider_ex=True, neighbor_cutoff=5.0, ex_conn
     return graph
 
 
-SCORE_COLUMNS = {1: 'DfScore1', 2: 'DfScore2', 3: 'DfScore3', 4: 'DfScore4', 5: 'DfScore5'}
+# column of an AncPhore .score line (tab separated, no header) by `fitness` (process_pharmacophore.py:885-925)
+SCORE_INDEX = {1: -4, 2: -3, 3: -2, 4: -1, 5: -5, 6: -6}
 
 
-def parse_score_file(score_file, fitness=1):
-    """AncPhore .score file -> list of fitness values (column chosen by `fitness`), None if unreadable."""
-    if not os.path.exists(score_file):
-        return None
-    rows = [l.rstrip('\n').split('\t') for l in open(score_file) if l.strip()]
-    if len(rows) < 2:
-        return None
-    col = SCORE_COLUMNS.get(fitness, 'DfScore1')
-    if col not in rows[0]:
-        return None
-    j = rows[0].index(col)
+def parse_score_file(score_file, return_all=False, fitness=1):
+    """AncPhore .score file -> one float per pose (column chosen by `fitness`), or the five columns [-6:-1] of every
+    pose with `return_all`.  None (after printing the reason) when the file cannot be parsed, like the reference."""
     try:
-        return [float(r[j]) for r in rows[1:]]
-    except (ValueError, IndexError):
+        lines = open(score_file).readlines()
+        if return_all:
+            return [[float(x) for x in line.strip().split('\t')[-6:-1]] for line in lines]
+        return [float(line.strip().split('\t')[SCORE_INDEX[fitness]]) for line in lines]
+    except Exception as e:
+        print(f'[E] Failed to parse the score file {score_file}.', e)
         return None
 
 
-def calc_phore_fitting(docked_file, phore_file, score_file, dbphore_file, log_file, overwrite=False, fitness=1,
-                       timeout=200):
-    """Scores the poses of `docked_file` against `phore_file` with the external AncPhore binary (black box, out of
-    scope to re-implement).  Returns the list of scores or None when the binary is unavailable / fails."""
-    if overwrite or not os.path.exists(score_file):
-        exe = os.environ.get('ANCPHORE', ANCPHORE)
-        if not (os.path.exists(exe) and os.access(exe, os.X_OK)):
-            return None
-        cmd = [exe, '-d', docked_file, '--refphore', phore_file, '--scores', score_file, 'usedMultiConformerFile', 'formodel']
+def calc_phore_fitting(ligand_file, phore_file, score_file, dbphore_file, log_file, overwrite=False, return_all=False,
+                       exVolume_cutoff=500, overlap_coeff=-1, percent_coeff=-1, anchor_coeff=-1, ancphore_path=ANCPHORE,
+                       target_fishing=False, fitness=1, timeout=200):
+    """Scores the poses of `ligand_file` against `phore_file` with the external AncPhore binary (a closed black box the
+    reference shells out to, process_pharmacophore.py:930-1000; same command line, run from the binary's directory).
+    Returns the parsed scores, or None when inputs / the binary are missing or no score file appears."""
+    ligand_file, phore_file, score_file, dbphore_file, log_file = (
+        os.path.abspath(p) for p in (ligand_file, phore_file, score_file, dbphore_file, log_file))
+    name = os.path.basename(ligand_file).split('.')[0]
+    ancphore_path = os.path.abspath(ancphore_path)
+    ok = True
+    for what, p in (('ligand file', ligand_file), ('pharmacophore file', phore_file)):
+        if not os.path.exists(p):
+            ok = False
+            print(f"[E] Failed to calculate the fitting score of ligand `{name}`.\nThe {what} `{p}` doesn't exist.")
+    if not os.path.exists(ancphore_path):
+        ok = False
+        print(f'[E] Invalid path to AncPhore program: `{ancphore_path}`')
+    fitness = 5 if target_fishing else fitness
+    if ok and (overwrite or not os.path.exists(score_file)):
+        cmd = [ancphore_path, '-d', ligand_file, '--refphore', phore_file, '--scores', score_file,
+               'usedMultiConformerFile', 'formodel']
+        if exVolume_cutoff != 500:
+            cmd += ['--exvolume_cutoff', str(exVolume_cutoff)]
+        for flag, v in (('--overlap_coeff', overlap_coeff), ('--percent_coeff', percent_coeff), ('--anchor_coeff', anchor_coeff)):
+            if v != -1:
+                cmd += [flag, str(v)]
+        if overwrite and os.path.exists(score_file):
+            os.remove(score_file)                                  # a stale file must not be parsed as this run's result
         try:
             with open(log_file, 'w') as lf:
-                subprocess.run(cmd, stdout=lf, stderr=subprocess.STDOUT, timeout=timeout, check=False)
-        except (subprocess.TimeoutExpired, OSError):
-            return None
-    return parse_score_file(score_file, fitness)
+                subprocess.run(cmd, stdout=lf, stderr=subprocess.STDOUT, timeout=timeout, check=False,
+                               cwd=os.path.dirname(ancphore_path))
+        except (subprocess.TimeoutExpired, OSError) as e:
+            print(f'[E] Failed to calculate the fitting score of ligand `{name}`.', e)
+    if os.path.exists(score_file):
+        return parse_score_file(score_file, return_all=return_all, fitness=fitness)
+    print(f'[E] No score file generated for {name} and {os.path.basename(phore_file)}')
+    return None

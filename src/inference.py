@@ -4,9 +4,9 @@
     python src/inference.py --phore examples/phore/X.phore --ligand examples/ligands/Y.sdf \
            --model_dir weights/diffphore_calibrated_warmuped_ft --out_dir results/run --sample_per_complex 40
 
-Differences by design: `fit` batches ACROSS pairs: all pending pairs x samples are denoised in
-HBM-sized chunks by one DenoisingSampler instead of one pair at a time; per-pair `run_time` is therefore the chunk
-time divided evenly over its pairs.  Preprocessing: RDKit path when RDKit is importable (not in this image), else the
+Differences by design: `fit` batches ACROSS pairs: pending pairs x samples are denoised in jobs of
+~4096 graphs by one DenoisingSampler instead of one pair at a time, and the SD writing + AncPhore scoring of a finished
+job overlaps the next job (PoseSink); per-pair `run_time` is the job time divided evenly over its pairs.  Preprocessing: RDKit path when RDKit is importable (not in this image), else the
 reduced RDKit-free featuriser for 3-D SD files (datasets/process_mols.py).  Scoring: AncPhore binary when available
 (`--ancphore_path`), else fitscore = -2.0 like the reference's failure sentinel (inference.py:235-237).
 """
@@ -67,6 +67,8 @@ def parse_args(argv=None):
     p.add_argument('--fitness', type=int, default=1)
     p.add_argument('--target_fishing', type=str2bool, default=False)
     p.add_argument('--seed', type=int, default=None, help='(new) seed of the device RNG; the reference is unseeded')
+    p.add_argument('--pairs_per_job', type=int, default=None, help='(new) pairs denoised together per GPU job; default: '
+                   'as many as give ~4096 graphs in flight and fit the resident HBM budget')
     args = p.parse_args(argv)
     if args.target_fishing:
         args.fitness = 5
@@ -115,66 +117,177 @@ def build_graph(record):
     return g
 
 
+def get_perfect_similarity(g, weights=(1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.0),
+                           alpha=(1.0, 1.0, 0.7, 1.0, 1.0, 0.7, 1.0, 1.0, 0.7, 1.0, 0.837)):
+    """Type/count-only pharmacophore fingerprint similarity used by --min_similarity (inference.py:273-312)."""
+    phore_volume = g['phore'].phoretype.sum(dim=0)
+    overlap = torch.min(g['ligand'].ph, phore_volume)
+    coeff = torch.tensor(weights).float()
+    if alpha is not None:
+        coeff = coeff * 7.999999999 * (torch.tensor(alpha) * torch.pi / 2) ** 1.5
+    weighted_volume = (phore_volume * coeff).sum()
+    if weighted_volume == 0:
+        return -1.0
+    return ((overlap * coeff).sum() / weighted_volume).item()
+
+
+class PoseSink:
+    """Pose output + scoring hand-off (calculate_fitscore, sampling.py:447-498; dock log, inference.py:242-246) off the
+    GPU's critical path: a thread pool writes `mapping_process/{name}/{name}.sdf`, runs the AncPhore binary
+    on it (a subprocess, so threads overlap), writes `ranked_poses/{name}_ranked.sdf` and `{name}_dock.log`, while the
+    next job of pairs is being denoised."""
+
+    def __init__(self, args, workers=8):
+        from concurrent.futures import ThreadPoolExecutor
+        self.args = args
+        self.pool = ThreadPoolExecutor(max_workers=max(1, workers))
+        self.pending = []
+
+    def submit(self, g, poses, run_time):
+        self.pending.append(self.pool.submit(self.process, g, poses, run_time))
+
+    def process(self, g, poses, run_time):
+        args, name, N = self.args, g.name, len(poses)
+        tmp = os.path.join(args.run_dir, f'mapping_process/{name}')
+        os.makedirs(tmp, exist_ok=True)
+        docked_file = os.path.join(tmp, f'{name}.sdf')
+        write_mol_with_multi_coords(g.sdf_template, poses, docked_file, name)
+        scores = calc_phore_fitting(docked_file, g.phore_file, os.path.join(tmp, f'{name}.score'),
+                                    os.path.join(tmp, f'{name}.dbphore'), os.path.join(tmp, f'{name}.log'),
+                                    overwrite=True, fitness=getattr(args, 'fitness', 1),
+                                    ancphore_path=os.path.join(args.ancphore_path, 'AncPhore'))
+        if scores is not None and len(scores) == N:
+            ranked_dir = os.path.join(args.run_dir, 'ranked_poses')
+            os.makedirs(ranked_dir, exist_ok=True)
+            perm = np.argsort(np.array(scores))[::-1]
+            write_mol_with_multi_coords(g.sdf_template, poses[perm], os.path.join(ranked_dir, f'{name}_ranked.sdf'), name,
+                                        marker='rank', properties={'fitscore': np.array(scores)[perm]})
+        json.dump({'name': name, 'fitscore': scores, 'run_time': run_time},
+                  open(os.path.join(tmp, f'{name}_dock.log'), 'w'), indent=4)
+        if scores is None or len(scores) == 0:
+            print(f'[W] fitscore calculated with error and set as -2.0 for `{name}`')
+            scores = [-2.0] * N
+        return name, scores, run_time
+
+    def drain(self):
+        """Results of everything submitted so far, in submission order."""
+        done, self.pending = [f.result() for f in self.pending], []
+        return done
+
+    def close(self):
+        self.pool.shutdown(wait=True)
+
+
+def plan_jobs(graphs, samples, pairs_cap, graphs_in_flight=4096):
+    """Cross-pair batching: consecutive pairs are grouped into jobs of about `graphs_in_flight`
+    (pair, sample) graphs — enough to fill 148 SMs with 256-edge tile pairs — and never more than `pairs_cap` pairs
+    (what fits the resident HBM budget).  The reference batches only the samples of ONE pair (inference.py:184, sampling.py:210)."""
+    per_job = max(1, min(pairs_cap, -(-graphs_in_flight // max(1, samples))))
+    return [graphs[k:k + per_job] for k in range(0, len(graphs), per_job)]
+
+
 def fit(args, model, complex_graphs, device, t_to_sigma, tmp_log='', n_report=1000):
+    """The reference's `fit` (inference.py:139-271) with its per-pair loop turned inside out: pairs that still need fitting are
+    denoised job by job (plan_jobs) with all their samples resident on the GPU, and every finished job is handed to the
+    PoseSink, which scores it while the next job runs.  Outputs, resume rule (:177-183, 248-252) and error rule (a failing
+    pair is reported and skipped, :211-222) are the reference's; `run_time` of a pair = its job's time / pairs in the job."""
     N = getattr(args, 'sample_per_complex', 1)
     so3n, torn = model.score_norm_tables()
     sampler = DenoisingSampler(model.kernel_weights(device), args.inference_steps, so3n, torn,
-                               no_final_step_noise=args.no_final_step_noise)
+                               no_final_step_noise=args.no_final_step_noise, ode=getattr(args, 'ode', False))
     gen = None
     if getattr(args, 'seed', None) is not None:
         gen = torch.Generator(device=device).manual_seed(args.seed)
-    names, fitscore, run_times = [], [], []
-    todo = []
+    keep = bool(getattr(args, 'keep_update', False))
+    done, todo = {}, []
     for g in complex_graphs:
+        if getattr(args, 'min_similarity', -1.0) > 0:
+            max_sim = get_perfect_similarity(g)
+            if max_sim < args.min_similarity:
+                print(f'[I] `{g.name}` is excluded due to pharmacophore fingerprint similarity constraints '
+                      f'({max_sim:.2f} < {args.min_similarity:.2f}).')
+                continue
         docked = os.path.join(args.run_dir, f'ranked_poses/{g.name}_ranked.sdf')
         log_file = os.path.join(args.run_dir, f'mapping_process/{g.name}/{g.name}_dock.log')
-        if os.path.exists(docked) and os.path.exists(log_file) and not args.overwrite:      # resume (inference.py:180-183)
+        if os.path.exists(docked) and os.path.exists(log_file) and not args.overwrite:
             log = json.load(open(log_file))
-            names.append(log['name']); fitscore.append(log['fitscore']); run_times.append(log['run_time'])
+            done[g.name] = (log['name'], log['fitscore'], log['run_time'])
         elif g['ligand'].pos.shape[0] == 0:
             print(f'[W] Graph {g.name} with 0 atoms, skipped')
         else:
             todo.append(g)
-    if todo:
+    sink = PoseSink(args, workers=min(getattr(args, 'num_workers', 8) or 1, os.cpu_count() or 1))
+    initial_poses, dock_poses = {}, {}
+    n_done, std_time = 0, time.time()
+
+    def run_job(job):
         t0 = time.time()
-        pos, ptr = sampler.run(todo, N, no_random=args.no_random, generator=gen, no_torsion=args.no_torsion)
-        run_time = (time.time() - t0) / len(todo)
-        for i, g in enumerate(todo):
-            n = g['ligand'].pos.shape[0]
-            poses = pos[ptr[i * N]:ptr[(i + 1) * N]].reshape(N, n, 3).numpy() + g.original_center.numpy()
-            tmp = os.path.join(args.run_dir, f'mapping_process/{g.name}')
-            os.makedirs(tmp, exist_ok=True)
-            docked_file = os.path.join(tmp, f'{g.name}.sdf')
-            write_mol_with_multi_coords(g.sdf_template, poses, docked_file, g.name)
-            os.environ.setdefault('ANCPHORE', os.path.join(args.ancphore_path, 'AncPhore'))
-            scores = calc_phore_fitting(docked_file, g.phore_file, os.path.join(tmp, f'{g.name}.score'),
-                                        os.path.join(tmp, f'{g.name}.dbphore'), os.path.join(tmp, f'{g.name}.log'),
-                                        overwrite=True, fitness=getattr(args, 'fitness', 1))
-            if not scores:
-                print(f'[W] fitscore calculated with error and set as -2.0 for `{g.name}`')
-                scores = [-2.0] * N
-            os.makedirs(os.path.join(args.run_dir, 'ranked_poses'), exist_ok=True)
-            perm = np.argsort(np.asarray(scores))[::-1]
-            write_mol_with_multi_coords(g.sdf_template, poses[perm], os.path.join(args.run_dir, f'ranked_poses/{g.name}_ranked.sdf'),
-                                        g.name, marker='rank', properties={'fitscore': np.asarray(scores)[perm]})
-            names.append(g.name); fitscore.append(list(map(float, scores))); run_times.append(run_time)
-            json.dump({'name': g.name, 'fitscore': list(map(float, scores)), 'run_time': run_time},
-                      open(os.path.join(tmp, f'{g.name}_dock.log'), 'w'), indent=4)
-    return {'name': names, 'fitscore': fitscore, 'run_time': run_times}
+        pos, ptr = sampler.run(job, N, no_random=args.no_random, generator=gen, no_torsion=args.no_torsion, keep_update=keep)
+        run_time = (time.time() - t0) / len(job)
+        for i, g in enumerate(job):
+            n, lo = g['ligand'].pos.shape[0], ptr[i * N]
+            center = g.original_center.numpy()
+            sink.submit(g, pos[lo:lo + N * n].reshape(N, n, 3).numpy() + center, run_time)
+            if keep:                                    # inference.py:191-192,247-248 (initial pose, pose after every step)
+                traj = sampler.last_trajectory[:, lo:lo + N * n].reshape(-1, N, n, 3).numpy()
+                initial_poses[g.name] = [traj[0, s] for s in range(N)]
+                dock_poses[g.name] = [[traj[k, s] for k in range(1, traj.shape[0])] for s in range(N)]
+
+    pairs_cap = sampler.graphs_per_chunk(todo, N) if todo else 1
+    jobs = plan_jobs(todo, N, getattr(args, 'pairs_per_job', None) or pairs_cap)
+    for job in jobs:
+        try:
+            run_job(job)
+        except Exception as e:                          # isolate the offending pair: rerun the job one pair at a time
+            if len(job) == 1:
+                print(f'[W] Error occured when fitting {job[0].name} to the reference pharamcophore, skipped. {e}')
+            for g in (job if len(job) > 1 else []):
+                try:
+                    run_job([g])
+                except Exception as e1:
+                    print(f'[W] Error occured when fitting {g.name} to the reference pharamcophore, skipped. {e1}')
+        n_done += len(job)
+        if tmp_log and n_done // n_report != (n_done - len(job)) // n_report:
+            print(f'[I] {n_done}/{len(todo)} processed...')
+            part = [done[k] for k in done] + [r for r in (f.result() for f in sink.pending if f.done())]
+            json.dump({'name': [r[0] for r in part], 'fitscore': [r[1] for r in part], 'run_time': [r[2] for r in part],
+                       'batch': n_done, 'total_time': time.time() - std_time}, open(tmp_log, 'w'), indent=4)
+    for r in sink.drain():
+        done[r[0]] = r
+    sink.close()
+    order = [g.name for g in complex_graphs if g.name in done]          # the reference reports in input order
+    metrics = {'name': order, 'fitscore': [done[k][1] for k in order], 'run_time': [done[k][2] for k in order]}
+    if keep:
+        metrics['initial_poses'] = [initial_poses.get(k) for k in order]
+        metrics['dock_poses'] = [dock_poses.get(k) for k in order]
+    return metrics
 
 
 def analyze_results(args, results):
+    """Summary table `ranked_results.csv` (tab separated; columns and ordering of inference.py:321-350)."""
     import pandas as pd
-    df = pd.DataFrame(results)
+    df = pd.DataFrame({k: results[k] for k in ('name', 'fitscore', 'run_time')})
     df['max_fitscore'] = df['fitscore'].map(lambda x: max(x) if len(x) else -2.0)
-    df['top5_mean_fitscore'] = df['fitscore'].map(lambda x: float(np.sort(x)[-5:].mean()))
+    df['top5_mean_fitscore'] = df['fitscore'].map(lambda x: np.sort(x)[-5:].mean().item())
     df['target'] = df['name'].map(lambda x: x.split('__')[0])
     df['ligand'] = df['name'].map(lambda x: x.split('__')[1])
     df = df.sort_values(by=['max_fitscore', 'top5_mean_fitscore'], ascending=False)
-    cols = ['target', 'ligand', 'max_fitscore', 'top5_mean_fitscore', 'run_time']
-    df[cols].to_csv(os.path.join(args.out_dir, 'ranked_results.csv'), index=False)
+    dump_file = os.path.join(args.out_dir, 'ranked_results.csv')
+    print(f'[I] Dumping results to `{dump_file}`')
+    df = df[['target', 'ligand', 'name', 'run_time', 'max_fitscore', 'top5_mean_fitscore', 'fitscore']]
+    df.to_csv(dump_file, sep='\t', index=False)
+    if args.cutoff is not None:
+        df[df['max_fitscore'] >= args.cutoff].to_csv(os.path.join(args.out_dir, f'ranked_results_gt{args.cutoff}.csv'),
+                                                     sep='\t', index=False)
     if args.report_results:
-        print(df[cols].head(20).to_string(index=False))
+        print()
+        print('#' * 25 + ' Pharmacophore Alignment Summary ' + '#' * 25)
+        for thr in (0.7, 0.4):
+            k = len(df[df['max_fitscore'] >= thr])
+            print(f'Number of ligands with fitscore greater than {thr}: {k} ({100 * k / len(df):.2f}%)')
+        print(f"Max fitscore: {df['max_fitscore'].max().item():.4f}")
+        print(f"Average max fitscore: {df['max_fitscore'].mean().item():.4f}")
+        print(f"Average runtime: {df['run_time'].mean().item():.4f}")
     return df
 
 
@@ -185,7 +298,8 @@ def main(argv=None):
     with open(f'{args.model_dir}/model_parameters.yml') as f:
         score_model_args = Namespace(**yaml.full_load(f))
     for k in ('sample_per_complex', 'inference_steps', 'actual_steps', 'ancphore_path', 'ode', 'no_torsion', 'no_random',
-              'no_final_step_noise', 'overwrite', 'min_similarity', 'keep_update', 'fitness', 'seed'):
+              'no_final_step_noise', 'overwrite', 'min_similarity', 'keep_update', 'fitness', 'seed', 'num_workers',
+              'pairs_per_job'):
         setattr(score_model_args, k, getattr(args, k))
     score_model_args.run_dir = args.out_dir
     t_to_sigma = partial(t_to_sigma_compl, args=score_model_args)
@@ -211,8 +325,16 @@ def main(argv=None):
         model.load_state_dict(state_dict, strict=True)
         model.eval()
         print('\n>> Starting to fit <<')
+        print(f"[I] Please check the process files in `{os.path.join(args.out_dir, 'mapping_process/')}`")
+        print(f"[I] Please check the ranked poses in `{os.path.join(args.out_dir, 'ranked_poses/')}`")
         results = fit(score_model_args, model, graphs, device, t_to_sigma, tmp_log=result_file + '.tmp')
-        json.dump(results, open(result_file, 'w'), indent=4)
+        if os.path.exists(result_file + '.tmp'):
+            os.remove(result_file + '.tmp')
+        if args.keep_update:
+            import pickle
+            pickle.dump(results, open(result_file + '.pkl', 'wb'))
+        else:
+            json.dump(results, open(result_file, 'w'), indent=4)
     else:
         results = json.load(open(result_file))
     if results and results['name']:

@@ -26,16 +26,19 @@ def randomize_position(data_list, no_torsion, no_random, tr_sigma_max, keep_upda
 def sampling_phore(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, device, t_to_sigma,
                    model_args, no_random=False, ode=False, visualization_list=None, confidence_model=None,
                    confidence_data_list=None, confidence_model_args=None, batch_size=20, no_final_step_noise=False):
-    if ode or confidence_model is not None or visualization_list is not None:
-        raise NotImplementedError('B200 path: Euler–Maruyama sampling without confidence model / visualisation only')
+    if confidence_model is not None or visualization_list is not None:
+        raise NotImplementedError('B200 path: sampling without confidence model / visualisation only')
     so3n, torn = model.score_norm_tables()
     sampler = DenoisingSampler(model.kernel_weights(device), inference_steps, so3n, torn,
-                               no_final_step_noise=no_final_step_noise)
+                               no_final_step_noise=no_final_step_noise, ode=ode)
+    keep = bool(getattr(model_args, 'keep_update', False))
     randomize = all('_dp_randomize' in g for g in data_list)
     pos, ptr = sampler.run(list(data_list), 1, no_random=no_random, randomize=randomize,
-                           no_torsion=getattr(model_args, 'no_torsion', False))
+                           no_torsion=getattr(model_args, 'no_torsion', False), keep_update=keep)
     for i, g in enumerate(data_list):
         g['ligand'].pos = pos[ptr[i]:ptr[i + 1]].clone()
+        if keep:                                            # diffusion_utils.py:71-77 (poses after every step)
+            g.docked_poses = [p.numpy() for p in sampler.last_trajectory[1:, ptr[i]:ptr[i + 1]]]
         g._attrs.pop('_dp_randomize', None)
     model.last_gpu_launches = sampler.gpu_launches
     return data_list, None

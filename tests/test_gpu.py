@@ -3,6 +3,8 @@
 Tolerances (fp32 everywhere, stated per SURVEY §8d): score-model outputs rel-L2 <= 1e-4 vs the fp32 oracle;
 one conformer update max-abs <= 2e-5 A; a 20-step trajectory with injected noise: final-coordinate RMSD <= 1e-4 A.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -422,9 +424,10 @@ def test_sampler_handles_ligands_without_rotatable_bonds_and_single_graph_jobs()
         assert torch.isfinite(a).all() and torch.equal(a, b)
 
 
-@pytest.mark.parametrize('mode', ['no_torsion', 'no_random'])
+@pytest.mark.parametrize('mode', ['no_torsion', 'no_random', 'ode'])
 def test_trajectory_flags_match_the_oracle(mode):
-    """--no_torsion (rigid-body updates only, sampling.py:246-250) and --no_random (zero noise, :230-244) against the oracle."""
+    """--no_torsion (rigid-body updates only, sampling.py:246-250), --no_random (zero noise, :230-244) and --ode
+    (0.5 g^2 dt score, no noise, :226-228,240-241) against the oracle; keep_update retains the pose after every step."""
     from diffphore_b200.engine import ModelWeights
     from diffphore_b200.sampler import DenoisingSampler
     from diffphore_b200.graph import collate
@@ -435,10 +438,10 @@ def test_trajectory_flags_match_the_oracle(mode):
     init, noise, n_rot = make_draws(graphs, S, 21, steps=steps)
     so3n, torn = So3ScoreNorm(), TorusScoreNorm()
     dl = oracle_initial_graphs(graphs, S, init, n_rot)
-    kw = dict(no_torsion=True, noise=noise) if mode == 'no_torsion' else dict(noise=None)
+    kw = dict(no_torsion=True, noise=noise) if mode == 'no_torsion' else dict(noise=None, ode=(mode == 'ode'))
     ref = osamp.sampling(dl, OracleScoreModel(sd, so3n, torn), steps, default_config(), collate, batch_size=S, **kw)
     ref_pos = torch.cat([g['ligand'].pos for g in ref])
-    smp = DenoisingSampler(ModelWeights(sd, torch.device('cuda:0')), steps, so3n, torn)
+    smp = DenoisingSampler(ModelWeights(sd, torch.device('cuda:0')), steps, so3n, torn, ode=(mode == 'ode'))
     if mode == 'no_torsion':
         # (the reference's randomize_position itself fails under --no_torsion when ligand.norm is present, sampling.py:50-53:
         #  [n,33] - [1,3]; so the initial poses are drawn with torsions and only the 20-step loop runs rigid-body updates)
@@ -447,6 +450,60 @@ def test_trajectory_flags_match_the_oracle(mode):
         smp.run_resident(resident, noise=noise, no_torsion=True)
         pos = torch.cat([b.pos for b, _, _, _ in resident]).cpu()
         ptr = np.concatenate([[0], np.cumsum(np.concatenate([b.n_per for b, _, _, _ in resident]))])
+    elif mode == 'ode':
+        pos, ptr = smp.run(graphs, S, init=init, noise=noise, keep_update=True)     # (noise must be ignored under --ode)
+        traj = smp.last_trajectory
+        assert traj.shape == (steps + 1, pos.shape[0], 3) and torch.equal(traj[-1], pos)
+        assert not torch.equal(traj[0], traj[1])
     else:
         pos, ptr = smp.run(graphs, S, init=init, no_random=True)
     assert max(_rmsd(pos, ref_pos, ptr)) <= 1e-4, _rmsd(pos, ref_pos, ptr)
+
+
+@needs_ckpt
+def test_inference_main_end_to_end_on_the_reference_example_files(tmp_path, capsys):
+    """cfg1 shape end to end through the mirrored CLI (src/inference.py main): the reference's example pharmacophore and three of
+    its example ligands from text files -> graphs -> cross-pair jobs on the GPU -> SD files -> (AncPhore when present) ->
+    inference_results.json / ranked_results.csv with the reference's layout; resume leaves finished pairs untouched."""
+    import json
+    import inference
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden/ingest.npz'))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    model_dir = os.path.join(root, 'oracle/_ref/weights')
+    if not os.path.exists(os.path.join(model_dir, 'model_parameters.yml')):
+        pytest.skip('model_parameters.yml not present')
+    (tmp_path / 'p.phore').write_text(str(gold['phore_text']))
+    names = ['STK936575', 'STK243239', 'STL432840']
+    rows = ['ligand_description,phore']
+    for nm in names:
+        (tmp_path / f'{nm}.sdf').write_text(str(gold[f'lig_text_{nm}']))
+        rows.append(f"{tmp_path / (nm + '.sdf')},{tmp_path / 'p.phore'}")
+    (tmp_path / 'task.csv').write_text('\n'.join(rows) + '\n')
+    anc = os.path.join(root, 'oracle/_ref/programs')
+    argv = ['--phore_ligand_csv', str(tmp_path / 'task.csv'), '--model_dir', model_dir, '--out_dir', str(tmp_path / 'out'),
+            '--sample_per_complex', '4', '--batch_size', '4', '--seed', '7', '--ancphore_path', anc, '--pairs_per_job', '2']
+    res = inference.main(argv)
+    assert res['name'] == [f'sQC_Substrate__{nm}' for nm in names] and all(len(f) == 4 for f in res['fitscore'])
+    have_anc = os.access(os.path.join(anc, 'AncPhore'), os.X_OK)
+    for nm, fs in zip(res['name'], res['fitscore']):
+        sdf = open(tmp_path / 'out' / 'mapping_process' / nm / f'{nm}.sdf').read()
+        assert sdf.count('$$$$') == 4 and 'nan' not in sdf
+        assert json.load(open(tmp_path / 'out' / 'mapping_process' / nm / f'{nm}_dock.log'))['name'] == nm
+        if have_anc:
+            assert all(-1e-6 <= f <= 1.0 for f in fs), fs
+            ranked = open(tmp_path / 'out' / 'ranked_poses' / f'{nm}_ranked.sdf').read()
+            tags = [float(l) for prev, l in zip(ranked.split('\n'), ranked.split('\n')[1:]) if prev.startswith('>  <fitscore>')]
+            assert tags == sorted(fs, reverse=True)
+        else:
+            assert fs == [-2.0] * 4
+    head = open(tmp_path / 'out' / 'ranked_results.csv').readline()
+    assert head == 'target\tligand\tname\trun_time\tmax_fitscore\ttop5_mean_fitscore\tfitscore\n'
+    assert json.load(open(tmp_path / 'out' / 'inference_results.json'))['fitscore'] == res['fitscore']
+    # resume (inference.py:177-183,248-252): finished pairs are read back from their dock logs, nothing is recomputed
+    if not have_anc:
+        return
+    os.remove(tmp_path / 'out' / 'inference_results.json')
+    stamp = os.path.getmtime(tmp_path / 'out' / 'mapping_process' / res['name'][0] / f"{res['name'][0]}.sdf")
+    res2 = inference.main(argv)
+    assert res2['fitscore'] == res['fitscore'] and res2['run_time'] == res['run_time']
+    assert os.path.getmtime(tmp_path / 'out' / 'mapping_process' / res['name'][0] / f"{res['name'][0]}.sdf") == stamp

@@ -1,0 +1,191 @@
+"""Data formats either side of the denoising path: `.phore` ingestion, rotatable-bond masks, AncPhore
+`.score` parsing and the pose-output SD writer, pinned against tests/golden/ingest.npz — outputs of the reference's own functions
+and its shipped example run (tools/make_ingest_golden.py).  CPU only."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'src'))
+import _bootstrap  # noqa: E402,F401
+from datasets import process_mols as pm              # noqa: E402
+from datasets import process_pharmacophore as pp     # noqa: E402
+from diffphore_b200.graph import HeteroGraph         # noqa: E402
+
+ANCPHORE = os.path.join(ROOT, 'oracle', '_ref', 'programs', 'AncPhore')
+
+
+@pytest.fixture(scope='module')
+def gold():
+    return np.load(os.path.join(ROOT, 'tests/golden/ingest.npz'))
+
+
+def test_phore_parser_and_graph_equal_the_reference(gold, tmp_path):
+    f = tmp_path / 'x.phore'
+    f.write_text(str(gold['phore_text']))
+    phores = pp.parse_phore(str(f))
+    assert len(phores) == 1 and phores[0].id == str(gold['phore_id'])
+    g = pp.get_phore_graph(phores[0], HeteroGraph(), consider_ex=True, neighbor_cutoff=5.0, ex_connected=True)
+    assert torch.equal(g['phore'].x, torch.from_numpy(gold['phore_x']))
+    assert torch.equal(g['phore'].pos, torch.from_numpy(gold['phore_pos']))
+    assert np.allclose(g['phore'].norm.numpy(), gold['phore_norm'], atol=1e-7)
+    assert np.array_equal(g['phore', 'phore_contact', 'phore'].edge_index.numpy(), gold['phore_edge_index'])
+    # skip_ex drops the exclusion spheres only
+    assert len(pp.parse_phore(str(f), skip_ex=True)[0].exclusion_volumes) == 0
+    with pytest.raises(FileNotFoundError):
+        pp.parse_phore(str(tmp_path / 'missing.phore'))
+    bad = tmp_path / 'bad.phore'
+    bad.write_text('id\nHA\t1.0\t2.0\n$$$$\n')
+    with pytest.raises(SyntaxError):
+        pp.parse_phore(str(bad))
+
+
+def test_transformation_mask_equals_the_reference_on_all_example_ligands(gold, tmp_path):
+    n_rot = 0
+    for nm in gold['lig_names']:
+        f = tmp_path / f'{nm}.sdf'
+        f.write_text(str(gold[f'lig_text_{nm}']))
+        g = pm.ligand_graph_from_sdf(str(f), HeteroGraph())
+        me, mr = g['ligand'].edge_mask.numpy(), g['ligand'].mask_rotate
+        assert np.array_equal(me, gold[f'mask_edges_{nm}']), nm
+        assert np.array_equal(mr, gold[f'mask_rotate_{nm}']), nm
+        ei = g['ligand', 'lig_bond', 'ligand'].edge_index.numpy()
+        assert np.array_equal(ei[:, 0::2], ei[::-1, 1::2])           # both directions consecutive (get_lig_graph)
+        for (u, v), row in zip(ei.T[me], mr):                         # the asserts of torsion.py:93-94
+            assert not row[u] and row[v]
+        n_rot += len(mr)
+    assert n_rot > 30
+
+
+def test_score_file_parser_equals_the_reference(gold, tmp_path, capsys):
+    f = tmp_path / 'x.score'
+    f.write_text(str(gold['score_text']))
+    for fit in range(1, 7):
+        assert np.array_equal(np.asarray(pp.parse_score_file(str(f), fitness=fit)), gold[f'score_fitness_{fit}'])
+    assert np.array_equal(np.asarray(pp.parse_score_file(str(f), return_all=True)), gold['score_all'])
+    assert pp.parse_score_file(str(tmp_path / 'missing.score')) is None          # prints, returns None (reference :921-923)
+    g = tmp_path / 'garbage.score'
+    g.write_text('a\tb\n')
+    assert pp.parse_score_file(str(g)) is None
+    assert '[E] Failed to parse' in capsys.readouterr().out
+
+
+def _read_records(path):
+    L = open(path).read().split('\n')
+    recs, i = [], 0
+    while i + 3 < len(L):
+        na, nb = int(L[i + 3][0:3]), int(L[i + 3][3:6])
+        xyz = np.asarray([[float(l[0:10]), float(l[10:20]), float(l[20:30])] for l in L[i + 4:i + 4 + na]])
+        elem = [l[31:34].strip() for l in L[i + 4:i + 4 + na]]
+        bonds = [(int(l[0:3]), int(l[3:6]), int(l[6:9])) for l in L[i + 4 + na:i + 4 + na + nb]]
+        j = i
+        while L[j] != '$$$$':
+            j += 1
+        recs.append(dict(name=L[i], xyz=xyz, elem=elem, bonds=bonds, tail=L[i + 4 + na + nb:j]))
+        i = j + 1
+    return recs
+
+
+def _template(gold, tmp_path):
+    f = tmp_path / 'STK936575.sdf'
+    f.write_text(str(gold['lig_text_STK936575']))
+    return pm.ligand_graph_from_sdf(str(f), HeteroGraph())
+
+
+def test_pose_writer_record_layout(gold, tmp_path):
+    g = _template(gold, tmp_path)
+    poses = gold['kat_poses']
+    out = tmp_path / 'docked.sdf'
+    pm.write_mol_with_multi_coords(g.sdf_template, poses, str(out), 'sQC_Substrate__STK936575')
+    recs = _read_records(str(out))
+    assert [r['name'] for r in recs] == list(gold['kat_record_names'])           # f"{name}_{marker}_{idx}" with marker ''
+    for r, p in zip(recs, poses):
+        assert np.array_equal(r['xyz'], np.round(p, 4)) and 'H' not in r['elem'] and len(r['bonds']) == 22
+    ranked = tmp_path / 'ranked.sdf'
+    fs = np.linspace(1, 0, len(poses))
+    pm.write_mol_with_multi_coords(g.sdf_template, poses, str(ranked), 'x', marker='rank', properties={'fitscore': fs})
+    recs = _read_records(str(ranked))
+    assert recs[3]['name'] == 'x_rank_3' and recs[3]['tail'][:3] == ['M  END', '>  <fitscore>  (4) ', f'{fs[3]}']
+
+
+@pytest.mark.skipif(not os.access(ANCPHORE, os.X_OK), reason='oracle/_ref/programs/AncPhore not present (build() copies it when '
+                    '/root/reference exists)')
+def test_pose_output_known_answer_through_ancphore(gold, tmp_path):
+    """The reference's shipped poses, written by OUR SD writer from the input ligand file, scored by the reference's AncPhore
+    binary against the shipped pharmacophore give the reference's shipped scores, to the printed digit, for every fitness column."""
+    g = _template(gold, tmp_path)
+    docked, phore = tmp_path / 'docked.sdf', tmp_path / 'ref.phore'
+    phore.write_text(str(gold['phore_text']))
+    pm.write_mol_with_multi_coords(g.sdf_template, gold['kat_poses'], str(docked), 'sQC_Substrate__STK936575')
+    args = (str(docked), str(phore), str(tmp_path / 'o.score'), str(tmp_path / 'o.dbphore'), str(tmp_path / 'o.log'))
+    for fit in range(1, 7):
+        scores = pp.calc_phore_fitting(*args, overwrite=(fit == 1), fitness=fit, ancphore_path=ANCPHORE)
+        assert scores is not None and np.array_equal(np.asarray(scores), gold[f'score_fitness_{fit}']), fit
+    assert np.array_equal(np.asarray(pp.calc_phore_fitting(*args, target_fishing=True, ancphore_path=ANCPHORE)),
+                          gold['score_fitness_5'])
+    # error behaviour: missing binary / missing inputs -> message + None (process_pharmacophore.py:960-970,995-998)
+    assert pp.calc_phore_fitting(str(docked), str(phore), str(tmp_path / 'p.score'), 'x', str(tmp_path / 'p.log'),
+                                 ancphore_path=str(tmp_path / 'nope')) is None
+
+
+@pytest.mark.skipif(not os.access(ANCPHORE, os.X_OK), reason='oracle/_ref/programs/AncPhore not present')
+def test_pose_sink_and_summary_reproduce_the_reference_example_run(gold, tmp_path, capsys):
+    """PoseSink (calculate_fitscore + dock log) and analyze_results on the reference's shipped poses reproduce the files of the
+    reference's shipped example run: per-pose fitscores, ranked SD file order / names / fitscore tags, ranked_results.csv."""
+    import json
+    from types import SimpleNamespace
+    import inference
+    g = _template(gold, tmp_path)
+    phore = tmp_path / 'sQC.phore'
+    phore.write_text(str(gold['phore_text']))
+    g.name, g.phore_file = 'sQC_Substrate__STK936575', str(phore)
+    run_dir = tmp_path / 'run'
+    args = SimpleNamespace(run_dir=str(run_dir), out_dir=str(run_dir), fitness=1, ancphore_path=os.path.dirname(ANCPHORE),
+                           cutoff=0.4, report_results=True)
+    sink = inference.PoseSink(args, workers=2)
+    sink.submit(g, gold['kat_poses'], 16.595691680908203)
+    (name, scores, run_time), = sink.drain()
+    sink.close()
+    assert name == g.name and np.array_equal(np.asarray(scores), gold['score_fitness_1'])
+    log = json.load(open(run_dir / 'mapping_process' / name / f'{name}_dock.log'))
+    assert log == {'name': name, 'fitscore': list(gold['score_fitness_1']), 'run_time': run_time}
+    recs = _read_records(str(run_dir / 'ranked_poses' / f'{name}_ranked.sdf'))
+    assert [r['name'] for r in recs] == list(gold['ranked_names'])
+    assert [r['tail'][2] for r in recs] == list(gold['ranked_fitscore_text'])
+    assert np.array_equal(np.asarray([r['xyz'][0] for r in recs]), gold['ranked_first_atom'])
+    inference.analyze_results(args, {'name': [name], 'fitscore': [scores], 'run_time': [run_time]})
+    assert open(run_dir / 'ranked_results.csv').read() == str(gold['ranked_results_text'])
+    assert open(run_dir / 'ranked_results_gt0.4.csv').read() == str(gold['ranked_results_text'])
+    assert 'Max fitscore: 0.4781' in capsys.readouterr().out
+
+
+def test_scoring_failure_sentinel_and_job_plan(gold, tmp_path, capsys):
+    from types import SimpleNamespace
+    import inference
+    g = _template(gold, tmp_path)
+    g.name, g.phore_file = 'a__b', str(tmp_path / 'missing.phore')
+    args = SimpleNamespace(run_dir=str(tmp_path / 'run'), fitness=1, ancphore_path=str(tmp_path))
+    sink = inference.PoseSink(args, workers=1)
+    sink.submit(g, gold['kat_poses'][:3], 1.0)
+    (name, scores, _), = sink.drain()
+    sink.close()
+    assert scores == [-2.0] * 3 and 'set as -2.0' in capsys.readouterr().out       # inference.py:235-237
+    assert not os.path.exists(tmp_path / 'run' / 'ranked_poses' / 'a__b_ranked.sdf')
+    jobs = inference.plan_jobs(list(range(1000)), 40, pairs_cap=10 ** 6)
+    assert [len(j) for j in jobs][:2] == [103, 103] and sum(len(j) for j in jobs) == 1000 and jobs[-1][-1] == 999
+    assert [len(j) for j in inference.plan_jobs(list(range(7)), 40, pairs_cap=3)] == [3, 3, 1]
+    assert [len(j) for j in inference.plan_jobs(list(range(3)), 10 ** 5, pairs_cap=8)] == [1, 1, 1]
+
+
+def test_perfect_similarity_matches_the_reference_formula():
+    import inference
+    g = HeteroGraph()
+    g['phore'].phoretype = torch.nn.functional.one_hot(torch.tensor([0, 1, 1, 4, 10, 10]), 11).float()
+    g['ligand'].ph = torch.tensor([1., 1, 0, 0, 3, 0, 0, 0, 0, 0, 0])
+    # weights 1 (EX 0), alpha 1 except AR/HY/CR: every counted type here has the same coefficient -> overlap 3 of volume 4
+    assert abs(inference.get_perfect_similarity(g) - 0.75) < 1e-6
+    g['phore'].phoretype = torch.nn.functional.one_hot(torch.tensor([10, 10]), 11).float()
+    assert inference.get_perfect_similarity(g) == -1.0
