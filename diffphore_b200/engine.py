@@ -169,7 +169,7 @@ class ModelWeights:
         if config:
             self.cfg.update(config)
         self.device = device = torch.device(device)
-        sd = state_dict
+        sd = {k: v.detach().cpu() for k, v in state_dict.items()}       # weight folding is host work (a model moved to CUDA hands CUDA tensors)
         self.lib = L.load()
         ns, nv = self.cfg['ns'], self.cfg['nv']
         if (ns, nv, self.cfg['num_conv_layers']) != (20, 10, 4):

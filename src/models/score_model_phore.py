@@ -200,7 +200,7 @@ class TensorProductScoreModel(nn.Module):
         if self._kernel_weights is None or self._kernel_weights.device != device:
             cfg = dict(lig_max_radius=self.lig_max_radius, cross_max_distance=self.cross_max_distance,
                        center_max_distance=self.center_max_distance, scaler=self.scaler, clash_cutoff=self.clash_cutoff)
-            self._kernel_weights = ModelWeights({k: v.detach() for k, v in self.state_dict().items()}, device, cfg)
+            self._kernel_weights = ModelWeights({k: v.detach().cpu() for k, v in self.state_dict().items()}, device, cfg)   # folding runs on the host
         return self._kernel_weights
 
     def score_norm_tables(self):

@@ -490,7 +490,7 @@ def test_inference_main_end_to_end_on_the_reference_example_files(tmp_path, caps
         assert sdf.count('$$$$') == 4 and 'nan' not in sdf
         assert json.load(open(tmp_path / 'out' / 'mapping_process' / nm / f'{nm}_dock.log'))['name'] == nm
         if have_anc:
-            assert all(-1e-6 <= f <= 1.0 for f in fs), fs
+            assert all(-1.0 <= f <= 1.0 for f in fs) and max(fs) > 0.05, fs      # (exclusion-volume clashes can push a pose below 0)
             ranked = open(tmp_path / 'out' / 'ranked_poses' / f'{nm}_ranked.sdf').read()
             tags = [float(l) for prev, l in zip(ranked.split('\n'), ranked.split('\n')[1:]) if prev.startswith('>  <fitscore>')]
             assert tags == sorted(fs, reverse=True)
