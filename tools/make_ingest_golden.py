@@ -90,6 +90,7 @@ def main():
     lig_dir = os.path.join(REF, 'examples/ligands')
     names = sorted(f[:-4] for f in os.listdir(lig_dir) if f.endswith('.sdf'))
     out['lig_names'] = np.asarray(names)
+    out['task_file_text'] = np.asarray(open(os.path.join(REF, 'examples/task_file.csv')).read())      # cfg3: 15 pairs
     for nm in names:
         elem, xyz, bonds = read_sdf(os.path.join(lig_dir, nm + '.sdf'))
         heavy = [i for i, e in enumerate(elem) if e != 'H']
