@@ -145,6 +145,36 @@ def _make_w1img(w1, b1):
     return img.contiguous().reshape(-1).view(torch.uint8), 2.0 ** (-k)
 
 
+TILE_GROUP = 8      # consecutive graphs whose nodes share one run of tiles (the greedy rule restarts at every group)
+
+
+def grouped_tiles(deg, nodes_per_graph, group=TILE_GROUP, cap=128):
+    """greedy_tiles restarted at every group of `group` consecutive graphs instead of at every graph, for ALL groups at once
+    (numpy, vectorised across groups; the walk over a group's nodes stays sequential like tile_walk in conv_fused.cuh).
+    deg: edge count of every node of the expanded batch, nodes_per_graph: [B].  Returns the first node of every tile
+    (global node indices, int64) or None if a node exceeds the cap."""
+    deg = np.asarray(deg, dtype=np.int64)
+    if deg.size and int(deg.max()) > cap:
+        return None
+    gstart = np.concatenate([[0], np.cumsum(nodes_per_graph)])[::group]
+    gend = np.append(gstart[1:], int(np.sum(nodes_per_graph)))
+    size = gend - gstart
+    M = int(size.max()) if size.size else 0
+    D = np.zeros((len(gstart), M), dtype=np.int64)
+    valid = np.arange(M)[None, :] < size[:, None]
+    D[valid] = deg
+    first = np.zeros_like(valid)
+    fill = np.zeros(len(gstart), dtype=np.int64)
+    opened = np.zeros(len(gstart), dtype=bool)
+    for j in range(M):
+        new = valid[:, j] & (~opened | (fill + D[:, j] > cap))
+        first[:, j] = new
+        fill = np.where(new, 0, fill) + D[:, j]
+        opened |= new
+    gi, ji = np.nonzero(first)
+    return gstart[gi] + ji
+
+
 def greedy_tiles(deg, cap=128):
     """Node-aligned tiles for dp_conv_fused: runs of whole output nodes with <= cap edges (same rule as
     tile_count_kernel / tile_fill_kernel).  deg: per-node edge counts of ONE graph.  Returns the first node of every
@@ -376,6 +406,10 @@ class PackedBatch:
         i32 = lambda t: t.to(torch.int32).contiguous()
         a0, p0 = atoms.gbase, phs.gbase                                # first atom / phore node of every graph
         self.lig_ptr, self.ph_ptr, self.rot_ptr = i32(a0), i32(p0), i32(rots.gbase)
+        # first atom / rotatable bond of every group of TILE_GROUP graphs (+ total): restart points of dp_build_tiles
+        self.n_groups = (B + TILE_GROUP - 1) // TILE_GROUP
+        self.lig_gptr = i32(torch.cat([a0[:-1:TILE_GROUP], a0[-1:]]))
+        self.rot_gptr = i32(torch.cat([rots.gbase[:-1:TILE_GROUP], rots.gbase[-1:]]))
         self.lig_batch = i32(atoms.graph)
         # ---- bonds (CSR by source atom), rotatable bonds, phore-phore edges (CSR by source node)
         bptr_c = cat_ptr = up(np.concatenate([q.bond_ptr[:-1] for q in pa]).astype(np.int64))
@@ -412,8 +446,24 @@ class PackedBatch:
             tn = up(np.concatenate([np.asarray(t, np.int64) for t in per_pair]))[lv.src] + node_base[lv.graph]
             return (i32(torch.cat([tn, torch.full((1,), n_nodes, **i64)])), None, lv.total)
 
-        self.tiles_cross_lig, self.tiles_cross_ph = tiles(t_lig, a0, self.n_lig), tiles(t_ph, p0, self.n_ph)
-        self.tiles_pp = tiles(t_pp, p0, self.n_ph)
+        def tiles_any(per_pair, node_base, n_nodes, deg_pair, nodes_pair):
+            """Per-graph tiles expanded on the device when they are (nearly) full anyway; otherwise tiles that span the graphs
+            of a group (grouped_tiles on the host, uploaded): sparse sets such as the phore-phore edges of an 8-point
+            pharmacophore (24 edges per graph) fill 4x fewer M = 128 operands that way."""
+            if any(t is None for t in per_pair):
+                return None
+            n_t = sum(len(t) for t in per_pair) * S
+            n_e = sum(int(np.sum(d)) for d in deg_pair) * S
+            if n_t == 0 or n_e >= 0.95 * cap_edges * n_t:
+                return tiles(per_pair, node_base, n_nodes)
+            deg = np.concatenate([np.tile(np.asarray(d, np.int64), S) for d in deg_pair])
+            tn = grouped_tiles(deg, np.repeat(nodes_pair, S))
+            return (i32(torch.cat([up(tn), torch.full((1,), n_nodes, **i64)])), None, len(tn))
+
+        cap_edges = 128
+        self.tiles_cross_lig = tiles_any(t_lig, a0, self.n_lig, [[q.P] * q.n for q in pa], n_p)
+        self.tiles_cross_ph = tiles_any(t_ph, p0, self.n_ph, [[q.n] * q.P for q in pa], P_p)
+        self.tiles_pp = tiles_any(t_pp, p0, self.n_ph, [np.diff(q.pp_ptr) for q in pa], P_p)
         # ---- mask_rotate rows (uint8) and their per-graph byte offsets
         msk = Level(nrot_p * n_p)
         self.mask = up(np.concatenate([q.mask.reshape(-1) for q in pa]).astype(np.uint8))[msk.src].contiguous() \
@@ -569,7 +619,7 @@ class Engine:
         ws.n_launches += 6
         ll_tiles = None
         if self.use_fused:
-            L.check(lib.dp_build_tiles(p(ws.ll_ptr), p(b.lig_ptr), b.B, p(ws.tile_cnt), p(ws.tile_start), p(ws.ll_tiles),
+            L.check(lib.dp_build_tiles(p(ws.ll_ptr), p(b.lig_gptr), b.n_groups, p(ws.tile_cnt), p(ws.tile_start), p(ws.ll_tiles),
                                        p(ws.ll_ntiles), st), 'dp_build_tiles')
             ws.n_launches += 3
             ll_tiles = (ws.ll_tiles, ws.ll_ntiles, ws.ll_tile_cap)
@@ -607,7 +657,7 @@ class Engine:
                                      p(ws.t_emb), p(ws.t_sh), p(ws.t_n), st), 'dp_tor_graph')
             tor_tiles = None
             if self.use_fused:
-                L.check(lib.dp_build_tiles(p(ws.t_ptr), p(b.rot_ptr), b.B, p(ws.tile_cnt), p(ws.tile_start), p(ws.tor_tiles),
+                L.check(lib.dp_build_tiles(p(ws.t_ptr), p(b.rot_gptr), b.n_groups, p(ws.tile_cnt), p(ws.tile_start), p(ws.tor_tiles),
                                            p(ws.tor_ntiles), st), 'dp_build_tiles')
                 ws.n_launches += 3
                 tor_tiles = (ws.tor_tiles, ws.tor_ntiles, ws.tor_tile_cap)

@@ -161,6 +161,24 @@ def test_greedy_tiles_rule():
     assert max(fill) <= 128 and all(f + deg[b] > 128 for f, b in zip(fill[:-1], t[1:-1]))   # greedy: the next node would not fit
 
 
+def test_grouped_tiles_equal_the_greedy_rule_restarted_per_group():
+    """engine.grouped_tiles (static edge sets; vectorised across groups) = greedy_tiles applied to every group of consecutive
+    graphs, the rule dp_build_tiles applies on the device to the dynamic edge sets."""
+    from diffphore_b200.engine import grouped_tiles, greedy_tiles
+    rng = np.random.default_rng(0)
+    for _ in range(40):
+        B = int(rng.integers(1, 30))
+        npg = rng.integers(0, 12, size=B)
+        deg = rng.integers(0, 60, size=int(npg.sum()))
+        G = int(rng.integers(1, 9))
+        off = np.concatenate([[0], np.cumsum(npg)])
+        exp = [off[g0] + t for g0 in range(0, B, G) for t in greedy_tiles(deg[off[g0]:off[min(g0 + G, B)]])]
+        assert list(grouped_tiles(deg, npg, group=G)) == exp
+    assert grouped_tiles([3, 129], [2]) is None
+    # 8-point pharmacophores with 24 edges: one tile per graph before, one per 5 graphs (120 edges) when tiles span graphs
+    assert len(grouped_tiles([3] * 8 * 16, [8] * 16, group=8)) == 4
+
+
 def test_fused_operand_images_reconstruct_the_weights():
     from diffphore_b200.engine import _make_w1img, _make_w2img112
     g = torch.Generator().manual_seed(0)
