@@ -12,10 +12,13 @@
 // kernel never materialises weights: report against the FLOP roofline").
 //
 // Work decomposition (one persistent CTA per SM, 352 threads, all 512 TMEM columns)
-//   * Edges are grouped by output node (CSR seg_ptr).  TILES are runs of whole nodes with <= 128 edges (tile_node[],
-//     built by dp_build_tiles or on the host), so the edge->node reduction never leaves the CTA: no atomics, the sum
-//     over a node's edges is sequential in edge order => bit-identical results for any batch composition.
-//   * The CTA processes PAIRS of tiles (256 edges): every weight chunk fetched from L2 by TMA feeds two M=128 MMA groups.
+//   * Edges are grouped by output node (CSR seg_ptr).  The unit of work is a PAIR TILE: a run of whole nodes with
+//     <= 256 edges (tile_node[], built by dp_build_tiles or on the host), so the edge->node reduction never leaves the
+//     CTA: no atomics, the sum over a node's edges is sequential in edge order => bit-identical results for any batch
+//     composition.  Its first 128 edges are MMA tile 0, the rest MMA tile 1 (a node may straddle the two: the reduction
+//     runs over the pair's 256 staged rows), so the node alignment costs half a node per 256 rows instead of per 128
+//     and nodes of up to 256 edges are supported (a 79-point pharmacophore: 3 atoms x 79 edges fill 237 of 256 rows).
+//   * Every weight chunk fetched from L2 by TMA feeds the two M=128 MMA groups of the pair.
 //     Warps 0-3 own the 128 TMEM lanes of tile 0, warps 4-7 those of tile 1 (thread = edge for the whole pair); warps
 //     8 / 9 issue the MMAs of tile 0 / 1 (converged warp, elect.sync-predicated asm: bare UTCHMMA in SASS), warp 10
 //     is the TMA producer.  Item 0 of a pair is the hidden layer (N = 64, weights = one 16 KB ring stage), items
@@ -70,7 +73,7 @@ struct ConvFusedArgs {
     const float* sh;
     int sh_stride;
     const int* seg_ptr;         // [n_out + 1]
-    const int* tile_node;       // [n_tiles + 1] first output node of every tile; tile_node[n_tiles] = n_out
+    const int* tile_node;       // [n_tiles + 1] first output node of every pair tile (<= 256 edges); tile_node[n_tiles] = n_out
     const int* n_tiles_dev;     // device tile count (dynamic graphs) or nullptr
     int n_tiles;
     const float* oscale;
@@ -303,7 +306,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
     // is provably warp-uniform.  With the tile count or the TMEM base in vector registers ptxas treats the issuing warp as
     // possibly divergent and brackets every UTCHMMA with ELECT / R2UR / VOTEU sequences that cost as much as the MMA itself.
     const int n_tiles = __reduce_max_sync(0xffffffffu, a.n_tiles_dev ? *a.n_tiles_dev : a.n_tiles);
-    const int n_pairs = (n_tiles + 1) >> 1;
+    const int n_pairs = n_tiles;                                      // one pair tile (2 x 128 MMA rows) per item of work
     if ((int)blockIdx.x >= n_pairs) return;
     const int my_pairs = (n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
@@ -357,9 +360,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
             const uint32_t idesc1 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // first layer: N = 64
             uint32_t g = 0, use = 0;                                        // use: items issued by this warp so far
             for (int pi = 0; pi < my_pairs; ++pi) {
-                const int pair = (int)blockIdx.x + pi * (int)gridDim.x;
-                const int ntile = (2 * pair + 1 < n_tiles) ? 2 : 1;
-                const bool mine = t < ntile;
+                constexpr bool mine = true;                             // (both MMA tiles of a pair tile always run; rows beyond its edges are zero)
                 const bool probe_on = pi == 1 && lane == 0 && t == 0;
                 int pidx = 0;
                 // barriers of one item: its weights landed, this tile's accumulator slot is drained
@@ -446,15 +447,15 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
         uint32_t item = 0;
         // indices of this thread's edge in pair `pr`: node range of the pair, first edge / edge count of its tile, gathered
         // node row, SH row
-        struct Idx { int n_lo, n_mid, n_hi, eb, ne, src, ce, ib, ic, ic2; };
+        struct Idx { int n_lo, n_hi, eb, ne, src, ce, ib, ic, ic2; };
         auto fetch = [&](int pr) {
             Idx x;
-            const int T0 = 2 * pr, nt = (T0 + 1 < n_tiles) ? 2 : 1;
-            x.n_lo = a.tile_node[T0]; x.n_mid = a.tile_node[T0 + 1]; x.n_hi = a.tile_node[T0 + nt];
-            x.eb = 0; x.ne = 0; x.src = -1; x.ce = 0; x.ib = 0; x.ic = 0; x.ic2 = -1;
-            if (tile < nt) {
-                x.eb = a.seg_ptr[tile ? x.n_mid : x.n_lo];
-                x.ne = a.seg_ptr[tile ? x.n_hi : x.n_mid] - x.eb;
+            x.n_lo = a.tile_node[pr]; x.n_hi = a.tile_node[pr + 1];
+            x.src = -1; x.ce = 0; x.ib = 0; x.ic = 0; x.ic2 = -1;
+            {
+                const int e0 = a.seg_ptr[x.n_lo], ne_pair = a.seg_ptr[x.n_hi] - e0;
+                x.eb = e0 + 128 * tile;                                  // MMA tile 0: edges 0..127 of the pair tile, tile 1: the rest
+                x.ne = min(max(ne_pair - 128 * tile, 0), 128);
                 if (row < x.ne) {
                     x.src = a.gather_idx ? a.gather_idx[x.eb + row] : x.eb + row;
                     x.ce = a.perm ? a.perm[x.eb + row] : x.eb + row;
@@ -512,9 +513,8 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
         load_attr(ix, at);
         for (int pi = 0; pi < my_pairs; ++pi) {
             const int pair = (int)blockIdx.x + pi * (int)gridDim.x;
-            const int ntile = (2 * pair + 1 < n_tiles) ? 2 : 1;
-            const bool active = tile < ntile;
-            if (ix.ne > 128) __trap();                                       // tile builder contract violated
+            constexpr int ntile = 2;
+            constexpr bool active = true;
             const bool valid = row < ix.ne;
             const bool probe_on = pi == 1 && tid == 0;
             CF_STAMP(1, 50, 0);
@@ -646,7 +646,8 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
             load_attr(nx, at);             // next pair's attributes (unconditional: `at` must not stay live across the main loop)
             CF_STAMP(1, 51, 0);
             {
-                const int e_lo = node_seg[0], e_mid = node_seg[ix.n_mid - ix.n_lo];
+                const int e_lo = node_seg[0];
+                if (node_seg[ix.n_hi - ix.n_lo] - e_lo > 256) __trap();      // tile builder contract violated
                 const int items = (ix.n_hi - ix.n_lo) * S::OQ;
                 // residual / running-sum operand of item `it` (loads issued one iteration ahead of their use)
                 auto load_add = [&](int it, float (&add)[4]) {
@@ -681,7 +682,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
                         const int nl = it / S::OQ, q = it % S::OQ, node = ix.n_lo + nl;
                         const int s0 = node_seg[nl], s1 = node_seg[nl + 1];
                         float* orow = a.out + (size_t)node * Cfg::D_OUT;
-                        const int r0 = node < ix.n_mid ? s0 - e_lo : 128 + s0 - e_mid;
+                        const int r0 = s0 - e_lo;                            // staged rows = the pair tile's edges in order
                         const float* sp = stg + (size_t)r0 * S::OS + 4 * q;
                         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
@@ -736,7 +737,7 @@ static int conv_fused_launch(const ConvFusedArgs& a, cudaStream_t st) {
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         attr_set = true;
     }
-    const int n_pairs = (a.n_tiles + 1) / 2;
+    const int n_pairs = a.n_tiles;
     const int grid = n_pairs < n_sm ? n_pairs : n_sm;
     if constexpr (Cfg::W == 2200) {
         if (a.dbg) {                                                       // profiling aid (tools/conv_fused_probe.py --stamps)
@@ -751,17 +752,18 @@ static int conv_fused_launch(const ConvFusedArgs& a, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Tile builder for dynamic graphs: greedy node-aligned packing (<= 128 edges per tile), restarted at every GROUP of
+// Tile builder for dynamic graphs: greedy node-aligned packing (<= 256 edges and <= 256 nodes per pair tile), restarted at every GROUP of
 // graphs (node_ptr holds the first node of every group; the engine groups 8 consecutive graphs) so that groups can be
 // processed in parallel (one thread per group), two passes around the exclusive scan.  Tiles may span graphs: a row of
 // the M = 128 MMA operand is one edge and rows are independent, so the per-node sums do not depend on the tiling
 // (bit-identical, tested); restarting at every graph instead left the last tile of every graph mostly empty
-// (cfg2: 5.2 -> 4.8 ligand-ligand tiles, 3.8 -> 3.4 torsion tiles per graph).  The degrees of 8 nodes are loaded
+// (cfg2: 5.2 -> 4.8 ligand-ligand M=128 operands, 3.8 -> 3.4 torsion operands per graph).  The node cap bounds node_seg[] in
+// shared memory (zero-degree nodes ride along with their neighbours).  The degrees of 8 nodes are loaded
 // together: the greedy rule is sequential, the loads are not.
 // ---------------------------------------------------------------------------------------------------------------
 template <class F>
 __device__ __forceinline__ void tile_walk(const int* __restrict__ seg_ptr, int n0, int n1, F&& on_tile) {
-    int fill = 0;
+    int fill = 0, nodes = 0;
     bool open = false;
     for (int nb = n0; nb < n1; nb += 8) {
         int s[9];
@@ -771,8 +773,9 @@ __device__ __forceinline__ void tile_walk(const int* __restrict__ seg_ptr, int n
         for (int j = 0; j < 8; ++j) {
             if (nb + j < n1) {
                 const int d = s[j + 1] - s[j];
-                if (!open || fill + d > 128) { on_tile(nb + j); fill = 0; open = true; }
+                if (!open || fill + d > 256 || nodes == 256) { on_tile(nb + j); fill = 0; nodes = 0; open = true; }
                 fill += d;
+                ++nodes;
             }
         }
     }

@@ -148,7 +148,10 @@ def _make_w1img(w1, b1):
 TILE_GROUP = 8      # consecutive graphs whose nodes share one run of tiles (the greedy rule restarts at every group)
 
 
-def grouped_tiles(deg, nodes_per_graph, group=TILE_GROUP, cap=128):
+TILE_EDGES = 256    # edges (and nodes) per pair tile of dp_conv_fused: two M = 128 MMA operands
+
+
+def grouped_tiles(deg, nodes_per_graph, group=TILE_GROUP, cap=TILE_EDGES):
     """greedy_tiles restarted at every group of `group` consecutive graphs instead of at every graph, for ALL groups at once
     (numpy, vectorised across groups; the walk over a group's nodes stays sequential like tile_walk in conv_fused.cuh).
     deg: edge count of every node of the expanded batch, nodes_per_graph: [B].  Returns the first node of every tile
@@ -165,29 +168,32 @@ def grouped_tiles(deg, nodes_per_graph, group=TILE_GROUP, cap=128):
     D[valid] = deg
     first = np.zeros_like(valid)
     fill = np.zeros(len(gstart), dtype=np.int64)
+    nodes = np.zeros(len(gstart), dtype=np.int64)
     opened = np.zeros(len(gstart), dtype=bool)
     for j in range(M):
-        new = valid[:, j] & (~opened | (fill + D[:, j] > cap))
+        new = valid[:, j] & (~opened | (fill + D[:, j] > cap) | (nodes == cap))
         first[:, j] = new
         fill = np.where(new, 0, fill) + D[:, j]
+        nodes = np.where(new, 0, nodes) + 1
         opened |= new
     gi, ji = np.nonzero(first)
     return gstart[gi] + ji
 
 
-def greedy_tiles(deg, cap=128):
-    """Node-aligned tiles for dp_conv_fused: runs of whole output nodes with <= cap edges (same rule as
-    tile_count_kernel / tile_fill_kernel).  deg: per-node edge counts of ONE graph.  Returns the first node of every
+def greedy_tiles(deg, cap=TILE_EDGES):
+    """Node-aligned pair tiles for dp_conv_fused: runs of whole output nodes with <= cap edges and <= cap nodes (same rule
+    as tile_walk in conv_fused.cuh).  deg: per-node edge counts of ONE graph (or group).  Returns the first node of every
     tile, or None if a single node exceeds the cap."""
-    first, fill = [], 0
+    first, fill, nodes = [], 0, 0
     for n, d in enumerate(deg):
         d = int(d)
         if d > cap:
             return None
-        if not first or fill + d > cap:
+        if not first or fill + d > cap or nodes == cap:
             first.append(n)
-            fill = 0
+            fill = nodes = 0
         fill += d
+        nodes += 1
     return first
 
 
@@ -438,7 +444,7 @@ class PackedBatch:
         self.cross_seg_ph = i32(excl(n_g[phs.graph]))
         del cg, cl_, ng, Pg, at, qt
 
-        # ---- node-aligned tiles of the static edge sets (dp_conv_fused); a node with > 128 edges: unfused kernels
+        # ---- node-aligned tiles of the static edge sets (dp_conv_fused); a node with > 256 edges: unfused kernels
         def tiles(per_pair, node_base, n_nodes):
             if any(t is None for t in per_pair):
                 return None
@@ -460,7 +466,7 @@ class PackedBatch:
             tn = grouped_tiles(deg, np.repeat(nodes_pair, S))
             return (i32(torch.cat([up(tn), torch.full((1,), n_nodes, **i64)])), None, len(tn))
 
-        cap_edges = 128
+        cap_edges = TILE_EDGES
         self.tiles_cross_lig = tiles_any(t_lig, a0, self.n_lig, [[q.P] * q.n for q in pa], n_p)
         self.tiles_cross_ph = tiles_any(t_ph, p0, self.n_ph, [[q.n] * q.P for q in pa], P_p)
         self.tiles_pp = tiles_any(t_pp, p0, self.n_ph, [np.diff(q.pp_ptr) for q in pa], P_p)

@@ -66,7 +66,7 @@ class DenoisingSampler:
                 eb = g['ligand', 'ligand'].edge_index.shape[1]
                 e_all = eb + n * min(n - 1, k + 1) + 2 * n * P + g['phore', 'phore'].edge_index.shape[1]
                 worst = max(worst, e_all * 4 * 60 + (n + P) * 4 * 600)      # edge embeddings / SH / indices + node features
-                if n > 128 or P > 128:                                      # a cross node with > 128 edges: unfused scratch too
+                if n > 256 or P > 256:                                      # a cross node with > 256 edges: unfused scratch too
                     worst = max(worst, n * P * 2200 * 4)
             return max(1, int(self.resident_bytes // (worst * samples)))
         worst = 1

@@ -326,10 +326,10 @@ def _conv_reference(layer, t):
 @pytest.mark.parametrize('layer', [0, 1, 2, 3, 5])
 def test_conv_fused_matches_float64_reference(built_lib, layer):
     """dp_conv_fused (tcgen05 MLP + thread-per-edge tensor product + in-CTA segmented mean) against a float64 evaluation of
-    fc -> e3nn FullyConnectedTensorProduct -> scatter-mean; irregular degrees incl. zero-degree nodes, a full 128-edge node
-    and an odd tile count (single-tile last pair)."""
+    fc -> e3nn FullyConnectedTensorProduct -> scatter-mean; irregular degrees incl. zero-degree nodes, nodes that fill one or
+    both MMA tiles of a pair tile (128, 256 edges), nodes that straddle the two MMA tiles, and a short last pair tile."""
     rng = np.random.default_rng(layer)
-    degs = np.concatenate([rng.integers(0, 40, 150), [128, 0, 1, 127, 3]])
+    degs = np.concatenate([rng.integers(0, 40, 150), [128, 0, 1, 127, 3, 256, 100, 79, 79, 79, 200, 5]])
     t = _conv_case(layer, degs, seed=layer)
     d_out = _CF[layer][1]
     t['oscale'], t['oshift'] = torch.ones(d_out), torch.zeros(d_out)          # identity affine map: plain tensor product
@@ -349,8 +349,9 @@ def test_conv_fused_is_bit_identical_under_tile_realignment(built_lib, layer):
 
 
 def test_conv_fused_modes_and_split_fallback_for_big_nodes(built_lib):
-    """mode 1 / mode 2 epilogues against mode 0, and a ligand with more than 128 atoms (phore nodes with > 128 cross edges):
-    the engine routes that edge set through the unfused kernels and still matches the oracle."""
+    """mode 1 / mode 2 epilogues against mode 0; a ligand with 140 atoms (phore nodes with 140 cross edges straddle the two MMA
+    tiles of a pair tile) and one with more than 256 atoms (phore nodes with > 256 cross edges: the engine routes that edge set
+    through the unfused kernels) still match the oracle."""
     rng = np.random.default_rng(1)
     degs = rng.integers(0, 30, 200)
     t = _conv_case(1, degs, seed=9)
@@ -361,8 +362,9 @@ def test_conv_fused_modes_and_split_fallback_for_big_nodes(built_lib):
     m2 = _run_conv_fused(1, t, built_lib, mode=2, out0=out0)
     assert torch.equal(m1[:, 50:], base[:, 50:]) and torch.allclose(m1[:, :50], base[:, :50] + res, atol=1e-6, rtol=1e-6)
     assert torch.allclose(m2, base + out0, atol=1e-6, rtol=1e-6)
-    r = run_forward_parity(n_pairs=1, n_atoms=140, n_phore=6, samples=1, weights='random', t=0.4, detail=True)
-    assert r['ok'], r
+    for n_atoms in (140, 260):
+        r = run_forward_parity(n_pairs=1, n_atoms=n_atoms, n_phore=6, samples=1, weights='random', t=0.4, detail=True)
+        assert r['ok'], r
 
 
 def test_cuda_graph_step_replay_is_bit_identical_to_eager_launches():

@@ -147,18 +147,20 @@ def test_step_constants_fold_the_sigma_embedding():
 # ---------------------------------------------------------------------------------------------------------------
 def test_greedy_tiles_rule():
     from diffphore_b200.engine import greedy_tiles
-    assert greedy_tiles([8] * 32) == [0, 16]                                   # 16 nodes x 8 edges fill a 128-edge tile
-    assert greedy_tiles([32] * 8) == [0, 4]
-    assert greedy_tiles([100, 0, 0, 28, 1]) == [0, 4]                          # zero-degree nodes ride along, 129th edge opens a tile
-    assert greedy_tiles([128, 128]) == [0, 1]
-    assert greedy_tiles([0, 0, 129]) is None                                   # a node with more than 128 edges: unfused kernels
+    assert greedy_tiles([8] * 64) == [0, 32]                                   # 32 nodes x 8 edges fill a 256-edge pair tile
+    assert greedy_tiles([32] * 16) == [0, 8]
+    assert greedy_tiles([200, 0, 0, 56, 1]) == [0, 4]                          # zero-degree nodes ride along, 257th edge opens a tile
+    assert greedy_tiles([256, 256]) == [0, 1]
+    assert greedy_tiles([79] * 7) == [0, 3, 6]                                 # 3 x 79 = 237 of 256 rows (79-point pharmacophore)
+    assert greedy_tiles([0, 0, 257]) is None                                   # a node with more than 256 edges: unfused kernels
+    assert greedy_tiles([0] * 600) == [0, 256, 512]                            # node cap: node_seg[] of the kernel holds 257 entries
     assert greedy_tiles([]) == []
     rng = np.random.default_rng(0)
     deg = rng.integers(0, 60, 500)
     t = greedy_tiles(deg) + [len(deg)]
     seg = np.concatenate([[0], np.cumsum(deg)])
     fill = [seg[b] - seg[a] for a, b in zip(t[:-1], t[1:])]
-    assert max(fill) <= 128 and all(f + deg[b] > 128 for f, b in zip(fill[:-1], t[1:-1]))   # greedy: the next node would not fit
+    assert max(fill) <= 256 and all(f + deg[b] > 256 for f, b in zip(fill[:-1], t[1:-1]))   # greedy: the next node would not fit
 
 
 def test_grouped_tiles_equal_the_greedy_rule_restarted_per_group():
@@ -174,9 +176,10 @@ def test_grouped_tiles_equal_the_greedy_rule_restarted_per_group():
         off = np.concatenate([[0], np.cumsum(npg)])
         exp = [off[g0] + t for g0 in range(0, B, G) for t in greedy_tiles(deg[off[g0]:off[min(g0 + G, B)]])]
         assert list(grouped_tiles(deg, npg, group=G)) == exp
-    assert grouped_tiles([3, 129], [2]) is None
-    # 8-point pharmacophores with 24 edges: one tile per graph before, one per 5 graphs (120 edges) when tiles span graphs
-    assert len(grouped_tiles([3] * 8 * 16, [8] * 16, group=8)) == 4
+    assert grouped_tiles([3, 257], [2]) is None
+    assert list(grouped_tiles([0] * 600, [600])) == [0, 256, 512]
+    # 8-point pharmacophores with 24 edges: one tile per graph when restarted per graph, one per group of 8 (192 edges) now
+    assert len(grouped_tiles([3] * 8 * 16, [8] * 16, group=8)) == 2
 
 
 def test_fused_operand_images_reconstruct_the_weights():
@@ -218,5 +221,4 @@ def test_packed_batch_expands_samples_like_a_naive_replication():
             assert np.array_equal(va, v), k
         elif k not in ('h2d_bytes', 'S', 'device'):
             assert va == v, k
-    assert a.tiles_cross_lig[2] == sum(-(-g['ligand'].pos.shape[0] * g['phore'].pos.shape[0] // 128) if
-                                       g['phore'].pos.shape[0] <= 128 else 0 for g in graphs) * S or a.tiles_cross_lig[2] > 0
+    assert a.tiles_cross_lig[2] > 0 and a.tiles_cross_lig[0].shape[0] == a.tiles_cross_lig[2] + 1
