@@ -184,6 +184,10 @@ def greedy_tiles(deg, cap=TILE_EDGES):
     """Node-aligned pair tiles for dp_conv_fused: runs of whole output nodes with <= cap edges and <= cap nodes (same rule
     as tile_walk in conv_fused.cuh).  deg: per-node edge counts of ONE graph (or group).  Returns the first node of every
     tile, or None if a single node exceeds the cap."""
+    deg = np.asarray(deg, dtype=np.int64)
+    if deg.size and deg.min() == deg.max():                    # uniform degrees (complete bipartite cross edges): closed form
+        d = int(deg[0])
+        return None if d > cap else list(range(0, len(deg), cap if d == 0 else min(cap // d, cap)))
     first, fill, nodes = [], 0, 0
     for n, d in enumerate(deg):
         d = int(d)
@@ -321,34 +325,38 @@ class ModelWeights:
 # =====================================================================================================================
 # batch packing
 # =====================================================================================================================
+def _np(t, dt):
+    """Tensor / array -> numpy of dtype dt without a copy when it already has it (host packing is on the e2e critical path)."""
+    a = t.numpy() if isinstance(t, torch.Tensor) and t.device.type == 'cpu' else (t.cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t))
+    return a if a.dtype == dt else a.astype(dt)
+
+
 def _pair_arrays(g):
     """numpy view of one HeteroGraph / PyG HeteroData pair in the kernels' layout (local indices)."""
     lig, ph = g['ligand'], g['phore']
     n = lig.pos.shape[0]
-    ei = g['ligand', 'ligand'].edge_index.cpu().numpy().astype(np.int64)
-    ea = g['ligand', 'ligand'].edge_attr.cpu().numpy()
+    ei = _np(g['ligand', 'ligand'].edge_index, np.int64)
+    ea = _np(g['ligand', 'ligand'].edge_attr, np.float32)
     btype = ea.argmax(1).astype(np.int32) if ea.size else np.zeros(0, np.int32)
-    mask = lig.edge_mask.cpu().numpy().astype(bool)
+    mask = _np(lig.edge_mask, np.bool_)
     order = np.argsort(ei[0], kind='stable')
     bond_ptr = np.zeros(n + 1, np.int32)
-    np.add.at(bond_ptr, ei[0] + 1, 1)
-    bond_ptr = np.cumsum(bond_ptr).astype(np.int32)
+    np.cumsum(np.bincount(ei[0], minlength=n), out=bond_ptr[1:])
     mr = lig.mask_rotate
-    mr = np.asarray(mr if isinstance(mr, np.ndarray) else mr[0]).astype(np.uint8).reshape(int(mask.sum()), n)
-    pe = g['phore', 'phore'].edge_index.cpu().numpy().astype(np.int64)
+    mr = _np(mr if isinstance(mr, (np.ndarray, torch.Tensor)) else mr[0], np.uint8).reshape(int(mask.sum()), n)
+    pe = _np(g['phore', 'phore'].edge_index, np.int64)
     po = np.argsort(pe[0], kind='stable')
     P = ph.pos.shape[0]
     pp_ptr = np.zeros(P + 1, np.int32)
-    np.add.at(pp_ptr, pe[0] + 1, 1)
+    np.cumsum(np.bincount(pe[0], minlength=P), out=pp_ptr[1:])
+    f32 = np.float32
     return SimpleNamespace(
-        n=n, P=P, x=lig.x.cpu().numpy().astype(np.int64), pos=lig.pos.cpu().numpy().astype(np.float32),
-        norm=lig.norm.cpu().numpy().astype(np.float32).reshape(n, 33), phorefp=lig.phorefp.cpu().numpy().astype(np.float32),
-        na1=lig.norm_angle1.cpu().numpy().astype(np.float32), na2=lig.norm_angle2.cpu().numpy().astype(np.float32),
+        n=n, P=P, x=_np(lig.x, np.int64), pos=_np(lig.pos, f32), norm=_np(lig.norm, f32).reshape(n, 33),
+        phorefp=_np(lig.phorefp, f32), na1=_np(lig.norm_angle1, f32), na2=_np(lig.norm_angle2, f32),
         bond_ptr=bond_ptr, bond_dst=ei[1][order].astype(np.int32), bond_type=btype[order],
         rot_u=ei[0][mask].astype(np.int32), rot_v=ei[1][mask].astype(np.int32), mask=mr,
-        px=ph.x.cpu().numpy().astype(np.float32), ppos=ph.pos.cpu().numpy().astype(np.float32),
-        pnorm=ph.norm.cpu().numpy().astype(np.float32), ptype=ph.phoretype.cpu().numpy().astype(np.float32),
-        pp_src=pe[0][po].astype(np.int32), pp_dst=pe[1][po].astype(np.int32), pp_ptr=np.cumsum(pp_ptr).astype(np.int32))
+        px=_np(ph.x, f32), ppos=_np(ph.pos, f32), pnorm=_np(ph.norm, f32), ptype=_np(ph.phoretype, f32),
+        pp_src=pe[0][po].astype(np.int32), pp_dst=pe[1][po].astype(np.int32), pp_ptr=pp_ptr)
 
 
 class PackedBatch:
@@ -379,8 +387,8 @@ class PackedBatch:
         n_p, P_p = np.asarray([q.n for q in pa]), np.asarray([q.P for q in pa])
         nrot_p, nb_p, npp_p = (np.asarray([len(q.rot_u) for q in pa]), np.asarray([len(q.bond_dst) for q in pa]),
                                np.asarray([len(q.pp_src) for q in pa]))
-        t_lig = [greedy_tiles([q.P] * q.n) for q in pa]
-        t_ph = [greedy_tiles([q.n] * q.P) for q in pa]
+        t_lig = [greedy_tiles(np.full(q.n, q.P)) for q in pa]
+        t_ph = [greedy_tiles(np.full(q.P, q.n)) for q in pa]
         t_pp = [greedy_tiles(np.diff(q.pp_ptr)) for q in pa]
         self.n_per, self.P_per, self.nrot_per = np.repeat(n_p, S), np.repeat(P_p, S), np.repeat(nrot_p, S)
         self.n_lig, self.n_ph, self.n_rot = int(n_p.sum()) * S, int(P_p.sum()) * S, int(nrot_p.sum()) * S
@@ -459,7 +467,7 @@ class PackedBatch:
             if any(t is None for t in per_pair):
                 return None
             n_t = sum(len(t) for t in per_pair) * S
-            n_e = sum(int(np.sum(d)) for d in deg_pair) * S
+            n_e = int(sum(int(d.sum()) for d in deg_pair)) * S
             if n_t == 0 or n_e >= 0.95 * cap_edges * n_t:
                 return tiles(per_pair, node_base, n_nodes)
             deg = np.concatenate([np.tile(np.asarray(d, np.int64), S) for d in deg_pair])
@@ -467,8 +475,8 @@ class PackedBatch:
             return (i32(torch.cat([up(tn), torch.full((1,), n_nodes, **i64)])), None, len(tn))
 
         cap_edges = TILE_EDGES
-        self.tiles_cross_lig = tiles_any(t_lig, a0, self.n_lig, [[q.P] * q.n for q in pa], n_p)
-        self.tiles_cross_ph = tiles_any(t_ph, p0, self.n_ph, [[q.n] * q.P for q in pa], P_p)
+        self.tiles_cross_lig = tiles_any(t_lig, a0, self.n_lig, [np.full(q.n, q.P) for q in pa], n_p)
+        self.tiles_cross_ph = tiles_any(t_ph, p0, self.n_ph, [np.full(q.P, q.n) for q in pa], P_p)
         self.tiles_pp = tiles_any(t_pp, p0, self.n_ph, [np.diff(q.pp_ptr) for q in pa], P_p)
         # ---- mask_rotate rows (uint8) and their per-graph byte offsets
         msk = Level(nrot_p * n_p)
