@@ -189,3 +189,64 @@ def test_perfect_similarity_matches_the_reference_formula():
     assert abs(inference.get_perfect_similarity(g) - 0.75) < 1e-6
     g['phore'].phoretype = torch.nn.functional.one_hot(torch.tensor([10, 10]), 11).float()
     assert inference.get_perfect_similarity(g) == -1.0
+
+
+class _FakeSampler:
+    """Stands in for DenoisingSampler in the host-logic test of inference.fit (no GPU): returns every input pose `samples` times,
+    fails for jobs containing a ligand named in `poison` (like a kernel error would)."""
+    poison, jobs = (), []
+
+    def __init__(self, *a, **kw):
+        self.kw = kw
+
+    def graphs_per_chunk(self, graphs, samples):
+        return 1000
+
+    def run(self, graphs, samples, keep_update=False, **kw):
+        _FakeSampler.jobs.append([g.name for g in graphs])
+        if any(g.name.split('__')[1] in _FakeSampler.poison for g in graphs):
+            raise RuntimeError('CUDA error: injected')
+        pos = torch.cat([g['ligand'].pos for g in graphs for _ in range(samples)])
+        ptr = np.concatenate([[0], np.cumsum([g['ligand'].pos.shape[0] for g in graphs for _ in range(samples)])])
+        self.last_trajectory = torch.stack([pos, pos + 1.0]) if keep_update else None
+        return pos, ptr
+
+
+def test_fit_host_logic_jobs_error_isolation_resume_and_keep_update(gold, tmp_path, monkeypatch, capsys):
+    """inference.fit around a stand-in sampler: cross-pair jobs, a failing job re-run pair by pair with the offending pair skipped
+    (inference.py:211-222), results in input order, resume from the dock logs (:177-183,248-252), keep_update trajectories."""
+    from types import SimpleNamespace
+    import inference
+    monkeypatch.setattr(inference, 'DenoisingSampler', _FakeSampler)
+    (tmp_path / 'p.phore').write_text(str(gold['phore_text']))
+    graphs = []
+    for nm in ['STK936575', 'STK243239', 'STL432840', 'STK255897', 'STK324209']:
+        f = tmp_path / f'{nm}.sdf'
+        f.write_text(str(gold[f'lig_text_{nm}']))
+        graphs.append(inference.build_graph({'ligand_description': str(f), 'phore': str(tmp_path / 'p.phore')}))
+    assert graphs[0].name == 'sQC_Substrate__STK936575' and graphs[0]['phore'].phoretype.shape == (79, 11)
+    assert torch.allclose(graphs[0]['phore'].pos.mean(0), torch.zeros(3), atol=1e-4)          # centred on the phore centroid
+    model = SimpleNamespace(score_norm_tables=lambda: (None, None), kernel_weights=lambda dev: None)
+    args = SimpleNamespace(run_dir=str(tmp_path / 'run'), sample_per_complex=3, inference_steps=2, no_final_step_noise=False,
+                           ode=False, seed=None, keep_update=True, min_similarity=-1.0, overwrite=False, no_random=False,
+                           no_torsion=False, num_workers=2, pairs_per_job=2, fitness=1,
+                           ancphore_path=os.path.dirname(ANCPHORE) if os.access(ANCPHORE, os.X_OK) else str(tmp_path))
+    _FakeSampler.poison, _FakeSampler.jobs = ('STL432840',), []
+    m = inference.fit(args, model, graphs, 'cpu', None)
+    names = [g.name for g in graphs]
+    assert _FakeSampler.jobs == [names[0:2], names[2:4], [names[2]], [names[3]], [names[4]]]   # job 2 failed -> pair by pair
+    assert m['name'] == [n for n in names if 'STL432840' not in n]                             # input order, bad pair skipped
+    assert 'STL432840 to the reference pharamcophore, skipped' in capsys.readouterr().out
+    assert all(len(f) == 3 for f in m['fitscore']) and len(m['dock_poses'][0]) == 3 and len(m['dock_poses'][0][0]) == 1
+    center = graphs[0].original_center.numpy()
+    # (the reference keeps both trajectories in the centred frame: inference.py:191-192, diffusion_utils.py:75-77)
+    assert np.allclose(m['initial_poses'][0][0], graphs[0]['ligand'].pos.numpy(), atol=1e-5)
+    assert np.allclose(m['dock_poses'][0][2][0], graphs[0]['ligand'].pos.numpy() + 1.0, atol=1e-5)
+    sdf = _read_records(str(tmp_path / 'run' / 'mapping_process' / names[0] / f'{names[0]}.sdf'))
+    assert len(sdf) == 3 and np.allclose(sdf[0]['xyz'], graphs[0]['ligand'].pos.numpy() + center, atol=1e-4)
+    if os.access(ANCPHORE, os.X_OK):
+        # resume: finished pairs come back from their dock logs, only the skipped pair is attempted again
+        _FakeSampler.poison, _FakeSampler.jobs = (), []
+        m2 = inference.fit(args, model, graphs, 'cpu', None)
+        assert _FakeSampler.jobs == [[names[2]]] and m2['name'] == names
+        assert [m2['fitscore'][i] for i in (0, 1, 3, 4)] == m['fitscore']
