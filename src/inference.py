@@ -291,9 +291,43 @@ def analyze_results(args, results):
     return df
 
 
+def _ranks():
+    """(rank, world, local_rank) from the torchrun environment; (0, 1, 0) for a plain `python src/inference.py`."""
+    return int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
+
+
+def merge_rank_results(parts, order):
+    """Per-rank result dicts of `fit` -> one dict in the input order of the pairs (`order`: all pair names)."""
+    rows = {}
+    for part in parts:
+        for i, name in enumerate(part['name']):
+            rows[name] = {k: v[i] for k, v in part.items()}
+    names = [n for n in order if n in rows]
+    keys = [k for k in (parts[0].keys() if parts else [])]
+    return {k: [rows[n][k] for n in names] for k in keys} if names else {'name': [], 'fitscore': [], 'run_time': []}
+
+
+def gather_results(results, all_names, world):
+    """The one exchange of a multi-rank run: every rank contributes the results table of its pairs, every rank gets the merged
+    table (a few floats per pose; gloo over TCP on the host - the poses themselves are already on disk)."""
+    import torch.distributed as dist
+    own_group = not dist.is_initialized()
+    if own_group:
+        dist.init_process_group('gloo')
+    parts = [None] * world
+    dist.all_gather_object(parts, results)
+    if own_group:
+        dist.destroy_process_group()
+    return merge_rank_results(parts, all_names)
+
+
 def main(argv=None):
+    """Single process: one GPU.  Under `torchrun --nproc-per-node N src/inference.py ...` the pairs are dealt round-robin to the N
+    ranks (one GPU each, SURVEY §8e: the path shards embarrassingly), every rank writes the SD files / dock logs of its own
+    pairs, and the only exchange is one gather of the per-pair results table at the end (gloo; poses never leave their rank)."""
     warnings.filterwarnings('ignore', category=UserWarning)
     args = parse_args(argv)
+    rank, world, local_rank = _ranks()
     result_file = os.path.join(args.out_dir, 'inference_results.json')
     with open(f'{args.model_dir}/model_parameters.yml') as f:
         score_model_args = Namespace(**yaml.full_load(f))
@@ -318,7 +352,10 @@ def main(argv=None):
         os.makedirs(args.out_dir, exist_ok=True)
         if not torch.cuda.is_available():
             raise RuntimeError('the B200 denoising path needs a CUDA device (there is no CPU fallback)')
-        device = torch.device('cuda')
+        device = torch.device('cuda', local_rank)
+        torch.cuda.set_device(device)
+        all_names = [g.name for g in graphs]
+        graphs = graphs[rank::world]                                        # this rank's pairs
         model = get_model(score_model_args, device, t_to_sigma=t_to_sigma, no_parallel=True)
         print(f'[I] Loading state dict from `{args.model_dir}/{args.ckpt}`')
         state_dict = torch.load(f'{args.model_dir}/{args.ckpt}', map_location=torch.device('cpu'), weights_only=False)
@@ -327,9 +364,15 @@ def main(argv=None):
         print('\n>> Starting to fit <<')
         print(f"[I] Please check the process files in `{os.path.join(args.out_dir, 'mapping_process/')}`")
         print(f"[I] Please check the ranked poses in `{os.path.join(args.out_dir, 'ranked_poses/')}`")
-        results = fit(score_model_args, model, graphs, device, t_to_sigma, tmp_log=result_file + '.tmp')
-        if os.path.exists(result_file + '.tmp'):
-            os.remove(result_file + '.tmp')
+        results = fit(score_model_args, model, graphs, device, t_to_sigma,
+                      tmp_log=result_file + ('.tmp' if world == 1 else f'.tmp{rank}'))
+        for tmp in (result_file + '.tmp', result_file + f'.tmp{rank}'):
+            if os.path.exists(tmp):
+                os.remove(tmp)
+        if world > 1:
+            results = gather_results(results, all_names, world)
+            if rank != 0:
+                return results
         if args.keep_update:
             import pickle
             pickle.dump(results, open(result_file + '.pkl', 'wb'))
@@ -337,7 +380,7 @@ def main(argv=None):
             json.dump(results, open(result_file, 'w'), indent=4)
     else:
         results = json.load(open(result_file))
-    if results and results['name']:
+    if rank == 0 and results and results['name']:
         analyze_results(args, results)
     return results
 
