@@ -8,7 +8,6 @@ so for already-3D SD files a REDUCED, RDKit-free featuriser is provided (heavy a
 perception by cycle basis, crude aromaticity / hybridisation / pharmacophore typing).  It yields the same tensor
 schema; chemical fidelity of the categorical features is not guaranteed (documented deviation).
 """
-import math
 import random
 
 import networkx as nx

@@ -11,10 +11,8 @@ reduced RDKit-free featuriser for 3-D SD files (datasets/process_mols.py).  Scor
 (`--ancphore_path`), else fitscore = -2.0 like the reference's failure sentinel (inference.py:235-237).
 """
 import _bootstrap  # noqa: F401  (repo root on sys.path)
-import copy
 import json
 import os
-import shutil
 import time
 import warnings
 from argparse import ArgumentParser, FileType, Namespace

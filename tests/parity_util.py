@@ -4,7 +4,6 @@ Used by tests/ (-m gpu), __graft_entry__.smoke() and tools/gpu_debug.py.  Tolera
   forward : rel-L2(tr), rel-L2(rot), rel-L2(tor) <= 1e-4 against the fp32 oracle
   update  : max |pos - pos_oracle| <= 2e-5 A for one conformer update
 """
-import copy
 import os
 import sys
 
