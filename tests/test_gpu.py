@@ -509,3 +509,31 @@ def test_inference_main_end_to_end_on_the_reference_example_files(tmp_path, caps
     res2 = inference.main(argv)
     assert res2['fitscore'] == res['fitscore'] and res2['run_time'] == res['run_time']
     assert os.path.getmtime(tmp_path / 'out' / 'mapping_process' / res['name'][0] / f"{res['name'][0]}.sdf") == stamp
+
+
+@pytest.mark.parametrize('shape', ['cfg1', 'cfg2', 'cfg4', 'cfg5'])
+def test_forward_matches_the_committed_frozen_oracle_outputs(shape):
+    """CUDA forward against tests/golden/oracle_frozen.npz (tools/make_oracle_frozen.py): the same seeded batch of every config
+    shape, compared with oracle outputs frozen in the repository instead of an oracle run on this box (rel-L2 <= 1e-4)."""
+    from diffphore_b200.engine import ModelWeights, Engine
+    from diffphore_b200.tables import So3ScoreNorm, TorusScoreNorm
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden/oracle_frozen.npz'))
+    kind, n_pairs, n_atoms, n_phore = {'cfg1': ('real', 1, 0, 0), 'cfg2': ('synthetic', 1, 32, 8), 'cfg4': ('synthetic', 1, 64, 12),
+                                       'cfg5': ('synthetic', 1, 128, 16)}[shape]
+    graphs = load_pairs(kind, n_pairs, n_atoms, n_phore)
+    init, _, n_rot = make_draws(graphs, 2, 3)
+    dl = oracle_initial_graphs(graphs, 2, init, n_rot)               # (host-side pose set-up only; no oracle forward here)
+    dev = torch.device('cuda:0')
+    cases = [('', random_state_dict(0))]
+    if shape == 'cfg1' and have_checkpoint() and 'cfg1_shipped_tr' in gold.files:
+        cases.append(('shipped_', real_state_dict()))
+    for tag, sd in cases:
+        w = ModelWeights(sd, dev)
+        eng = Engine(w)
+        b, ws = eng.pack(dl, 1)
+        sc = w.step_consts(0.6, So3ScoreNorm(), TorusScoreNorm(seed=0), dt=0.05).to(dev)
+        tr, rot, tor = eng.forward(b, ws, sc)
+        torch.cuda.synchronize()
+        for key, val in (('tr', tr), ('rot', rot), ('tor', tor[:b.n_rot])):
+            ref = gold[f'{shape}_{tag}{key}']
+            assert rel(val.cpu(), ref) <= 1e-4, (shape, tag, key, rel(val.cpu(), ref))

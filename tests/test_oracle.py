@@ -253,3 +253,23 @@ def test_oracle_sampling_loop_runs_and_is_deterministic():
     res0 = osamp.sampling(oracle_initial_graphs(graphs, 2, init, n_rot), OracleScoreModel(sd, *tabs), 2, default_config(),
                           collate, batch_size=3, noise=None)
     assert not torch.equal(torch.cat([g['ligand'].pos for g in res0]), outs[0])       # no_random differs from noisy run
+
+
+def test_oracle_reproduces_its_frozen_outputs():
+    """tests/golden/oracle_frozen.npz (tools/make_oracle_frozen.py): forward outputs for one seeded batch of every config shape
+    (cfg1 real-shaped P = 79, cfg2 32/8, cfg4 64/12, cfg5 128/16), a 20-step trajectory with injected draws, and the so3 / torus
+    score norms of the 20-step schedule.  Guards the checker itself: an edit of oracle/ that moves any of these is caught here."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('make_oracle_frozen', os.path.join(ROOT, 'tools', 'make_oracle_frozen.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'oracle_frozen.npz'))
+    now = mod.build()
+    for k in gold.files:
+        if k not in now:                                   # cfg1_shipped_* without the checkpoint
+            assert k.startswith('cfg1_shipped_') and not have_checkpoint()
+            continue
+        if k == 'traj_pos':
+            assert float(np.abs(now[k] - gold[k]).max()) <= 1e-3, k          # 20 chained steps (fp32 summation order may differ per host)
+        else:
+            assert rel(now[k], gold[k]) <= 1e-5, (k, rel(now[k], gold[k]))
