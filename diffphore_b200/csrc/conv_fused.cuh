@@ -34,6 +34,7 @@
 //     node rows gathered under the first chunk MMAs -> chunk loop -> rows staged as float4 -> per-(node, quad)
 //     sequential sums, mean, BatchNorm scale/shift, residual.
 #pragma once
+#include <type_traits>
 #include "edge_mlp_tc.cuh"
 #include "tp_tables.cuh"
 
@@ -52,6 +53,20 @@
 // profiling aid (tools/conv_fused_probe.py --stamps): clock64() stamps of CTA 0, second pair; role 0 = MMA issuer,
 // 1 = warp 0, 2 = warp 4; [role][item (< 64)][3]
 #define CF_STAMP(role, idx, k) do { if (PROBE && blockIdx.x == 0 && probe_on && (idx) < 64) a_dbg[((role) * 64 + (idx)) * 3 + (k)] = clock64(); } while (0)
+
+// EXPERIMENTAL weight-column layout (dp_conv_fused_flat; not the default, not yet validated on hardware): the W columns of the
+// e3nn weight layout are cut into consecutive 112-column chunks regardless of the path boundaries ("flat"), so that only the
+// last chunk carries zero padding: ceil(W / 112) chunks instead of W / 100 chunks of 112 (2200 columns: 20 instead of 22 MMA
+// groups, 9 % less issued tensor-pipe work).  The per-column work is generated from compile-time column -> (path, row, channel)
+// maps, so the accumulation order (paths, then weight rows, in e3nn order) and every product are those of the path-aligned layout.
+template <class Base>
+struct CfFlat : Base {
+    static constexpr bool FLAT = true;
+};
+template <class Cfg, class = void>
+struct cf_is_flat { static constexpr bool value = false; };
+template <class Cfg>
+struct cf_is_flat<Cfg, std::enable_if_t<Cfg::FLAT>> { static constexpr bool value = true; };
 
 struct ConvFusedArgs {
     // first MLP layer: attr(e) = [emb[perm[e]] | tb[idxB[e], 0:20] | tc[idxC[e], 0:20] (+ tc[idxC2[e], 0:20])]
@@ -283,12 +298,83 @@ __device__ __forceinline__ void cf_paths(uint32_t tmem_lane_base, uint64_t* t_fu
     }
 }
 
+// ---- flat layout (CfFlat<Cfg>): chunk C holds weight columns [112 C, 112 C + 112) of the e3nn layout ----
+template <class Cfg>
+__host__ __device__ constexpr int cf_path_of(int g) {                    // path that owns weight column g
+    for (int pi = 0; pi < Cfg::NP; ++pi) {
+        const TpPath p = Cfg::paths[pi];
+        if (g >= p.w_off && g < p.w_off + p.U * Cfg::outs[p.oi].V) return pi;
+    }
+    return 0;
+}
+template <class Cfg, int C>
+struct CfFlatChunk {
+    static constexpr int G0 = C * CF_N;
+    static constexpr int NV = (Cfg::W - G0) < CF_N ? (Cfg::W - G0) : CF_N;            // valid columns of this chunk (even)
+};
+// columns COL, COL + 1 of chunk C (one FFMA2 per output component), then the rest of the chunk
+template <class Cfg, int C, int COL>
+__device__ __forceinline__ void cf_flat_cols(uint32_t tslot, float (&wv)[2][16], float2 (&zz)[3], const float* __restrict__ xrow,
+                                             const float* shv, float2 (&acc)[Cfg::D_OUT / 2]) {
+    using CH = CfFlatChunk<Cfg, C>;
+    if constexpr (COL < CH::NV) {
+        constexpr int q = COL / 16, j = COL % 16;
+        if constexpr (j == 0) {
+            cf_wait_ld16(wv[q & 1]);
+            if constexpr (16 * (q + 1) < CH::NV) cf_tmem_ld16(tslot + 16 * (q + 1), wv[(q + 1) & 1]);
+        }
+        constexpr int g = CH::G0 + COL;
+        constexpr TpPath p = Cfg::paths[cf_path_of<Cfg>(g)];
+        constexpr TpOut o = Cfg::outs[p.oi];
+        constexpr int V = o.V, K = 2 * o.lo + 1, D1 = 2 * p.l1 + 1, r = (g - p.w_off) / V, v = (g - p.w_off) % V;
+        static_assert(V % 2 == 0 && o.off % 2 == 0 && p.w_off % 2 == 0 && CF_N % 2 == 0, "channel pairs must not straddle rows or chunks");
+        if constexpr (v == 0 || COL == 0) {                                // next weight row (or a row continued from the previous chunk)
+            float xv[3], z[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < D1; ++i) xv[i] = xrow[p.in_off + r * D1 + i];
+            dp_cg<p.l1, p.l2, o.lo>(xv, shv + p.sh_off, z);
+#pragma unroll
+            for (int k = 0; k < K; ++k) zz[k] = make_float2(z[k], z[k]);
+        }
+        const float2 w2 = make_float2(wv[q & 1][j], wv[q & 1][j + 1]);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float2& a2 = acc[o.off / 2 + k * (V / 2) + v / 2];
+            a2 = __ffma2_rn(w2, zz[k], a2);
+        }
+        cf_flat_cols<Cfg, C, COL + 2>(tslot, wv, zz, xrow, shv, acc);
+    }
+}
+template <class Cfg, int C, int END>
+__device__ __forceinline__ void cf_flat_chunks(uint32_t tmem_lane_base, uint64_t* t_full, uint64_t* t_empty, uint32_t& item, int tile,
+                                               const float* __restrict__ xrow, const float* shv, float2 (&acc)[Cfg::D_OUT / 2], int lane) {
+    if constexpr (C < END) {
+        const uint32_t it = item, slot = 2 * (it & 1) + (uint32_t)tile, use = it >> 1;
+        if (lane == 0) tc_mbar_wait(&t_full[slot], use & 1);
+        __syncwarp();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+            const uint32_t tslot = tmem_lane_base + slot * CF_SLOT_COLS;
+            float wv[2][16];
+            float2 zz[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+            cf_tmem_ld16(tslot, wv[0]);
+            cf_flat_cols<Cfg, C, 0>(tslot, wv, zz, xrow, shv, acc);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tc_mbar_arrive(&t_empty[slot]);
+        ++item;
+        cf_flat_chunks<Cfg, C + 1, END>(tmem_lane_base, t_full, t_empty, item, tile, xrow, shv, acc, lane);
+    }
+}
+
 template <class Cfg, bool PROBE>
 __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs a) {
     long long* const a_dbg = a.dbg;
     using S = ConvFusedSmem<Cfg>;
-    constexpr int NCH = Cfg::W / CF_CHUNK;
-    static_assert(Cfg::W % CF_CHUNK == 0, "W must be a multiple of the chunk");
+    constexpr bool FLAT = cf_is_flat<Cfg>::value;
+    constexpr int NCH = FLAT ? (Cfg::W + CF_N - 1) / CF_N : Cfg::W / CF_CHUNK;
+    static_assert(FLAT || Cfg::W % CF_CHUNK == 0, "W must be a multiple of the chunk");
     extern __shared__ __align__(1024) uint8_t cf_smem_raw[];
     uint8_t* b_st = cf_smem_raw;                                                    // STAGES x (hi | lo)
     uint8_t* alo = b_st + S::STAGES * CF_B_STAGE;                                   // 2 tiles x [k/8][m/8][m%8][k%8] fp16 (A lo)
@@ -628,10 +714,16 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
             // The next pair's indices are a chain of three dependent global loads (tile -> segment -> edge level).  Inside the
             // chunk loop its stalls are free: the workers drain a chunk in about half the time the tensor pipe needs for it.
             const uint32_t item0 = item;
-            cf_paths<Cfg, 0, 1, PROBE>(lane_base, t_full, t_empty, item, tile, ntile, active, xrow, shv, acc, lane, pi == 1, item0, a_dbg);
             Idx nx = ix;
-            if (pi + 1 < my_pairs) nx = fetch(pair + (int)gridDim.x);
-            cf_paths<Cfg, 1, Cfg::NP, PROBE>(lane_base, t_full, t_empty, item, tile, ntile, active, xrow, shv, acc, lane, pi == 1, item0, a_dbg);
+            if constexpr (FLAT) {
+                cf_flat_chunks<Cfg, 0, 4>(lane_base, t_full, t_empty, item, tile, xrow, shv, acc, lane);
+                if (pi + 1 < my_pairs) nx = fetch(pair + (int)gridDim.x);
+                cf_flat_chunks<Cfg, 4, NCH>(lane_base, t_full, t_empty, item, tile, xrow, shv, acc, lane);
+            } else {
+                cf_paths<Cfg, 0, 1, PROBE>(lane_base, t_full, t_empty, item, tile, ntile, active, xrow, shv, acc, lane, pi == 1, item0, a_dbg);
+                if (pi + 1 < my_pairs) nx = fetch(pair + (int)gridDim.x);
+                cf_paths<Cfg, 1, Cfg::NP, PROBE>(lane_base, t_full, t_empty, item, tile, ntile, active, xrow, shv, acc, lane, pi == 1, item0, a_dbg);
+            }
             CF_STAMP(1, 50, 2);
             // ---- epilogue: per-edge results -> smem (aliases the node rows), segmented mean + BatchNorm + residual ----
             cf_bar_workers();                                              // every worker is done with its node row

@@ -149,7 +149,7 @@ static long long* g_cf_dbg_host = nullptr;
 /* profiling aid (not part of the public header): per-phase clock stamps of dp_conv_fused (layer 3) */
 int dp_debug_set_cf_probe(long long* buf) { g_cf_dbg_host = buf; return DP_OK; }
 
-int dp_conv_fused(int32_t layer, const float* emb, const int32_t* perm, const float* tb, const int32_t* idxB, int32_t strideB,
+static int conv_fused_dispatch(bool flat, int32_t layer, const float* emb, const int32_t* perm, const float* tb, const int32_t* idxB, int32_t strideB,
                   const float* tc, const int32_t* idxC, const int32_t* idxC2, int32_t strideC, const void* w1img,
                   float inv_w1scale, const void* w2img, float inv_wscale, const float* node_in, const int32_t* gather_idx,
                   const float* sh, int32_t sh_stride, const int32_t* seg_ptr, const int32_t* tile_node,
@@ -167,6 +167,18 @@ int dp_conv_fused(int32_t layer, const float* emb, const int32_t* perm, const fl
     a.n_tiles = n_tiles_cap; a.oscale = oscale; a.oshift = oshift; a.out = out; a.residual = residual; a.res_dim = res_dim;
     a.mode = mode;
     a.dbg = g_cf_dbg_host;
+    if (flat) {
+        a.dbg = nullptr;
+        switch (layer) {
+            case DP_TP_L0: return conv_fused_launch<CfFlat<TpL0>>(a, ST(stream));
+            case DP_TP_L1: return conv_fused_launch<CfFlat<TpL1>>(a, ST(stream));
+            case DP_TP_L2: return conv_fused_launch<CfFlat<TpL2>>(a, ST(stream));
+            case DP_TP_L3: return conv_fused_launch<CfFlat<TpL3>>(a, ST(stream));
+            case DP_TP_TOR: return conv_fused_launch<CfFlat<TpTor>>(a, ST(stream));
+        }
+        dp_set_error("dp_conv_fused_flat: unsupported layer %d", layer);
+        return DP_ERR_ARG;
+    }
     switch (layer) {
         case DP_TP_L0: return conv_fused_launch<TpL0>(a, ST(stream));
         case DP_TP_L1: return conv_fused_launch<TpL1>(a, ST(stream));
@@ -176,6 +188,28 @@ int dp_conv_fused(int32_t layer, const float* emb, const int32_t* perm, const fl
     }
     dp_set_error("dp_conv_fused: unsupported layer %d", layer);
     return DP_ERR_ARG;
+}
+
+int dp_conv_fused(int32_t layer, const float* emb, const int32_t* perm, const float* tb, const int32_t* idxB, int32_t strideB,
+                  const float* tc, const int32_t* idxC, const int32_t* idxC2, int32_t strideC, const void* w1img,
+                  float inv_w1scale, const void* w2img, float inv_wscale, const float* node_in, const int32_t* gather_idx,
+                  const float* sh, int32_t sh_stride, const int32_t* seg_ptr, const int32_t* tile_node,
+                  const int32_t* n_tiles_dev, int32_t n_tiles_cap, const float* oscale, const float* oshift, float* out,
+                  const float* residual, int32_t res_dim, int32_t mode, void* stream) {
+    return conv_fused_dispatch(false, layer, emb, perm, tb, idxB, strideB, tc, idxC, idxC2, strideC, w1img, inv_w1scale, w2img,
+                               inv_wscale, node_in, gather_idx, sh, sh_stride, seg_ptr, tile_node, n_tiles_dev, n_tiles_cap, oscale,
+                               oshift, out, residual, res_dim, mode, stream);
+}
+/* EXPERIMENTAL: same contract, second-layer weights in the flat 112-column layout (engine._make_w2imgflat) */
+int dp_conv_fused_flat(int32_t layer, const float* emb, const int32_t* perm, const float* tb, const int32_t* idxB, int32_t strideB,
+                       const float* tc, const int32_t* idxC, const int32_t* idxC2, int32_t strideC, const void* w1img,
+                       float inv_w1scale, const void* w2img, float inv_wscale, const float* node_in, const int32_t* gather_idx,
+                       const float* sh, int32_t sh_stride, const int32_t* seg_ptr, const int32_t* tile_node,
+                       const int32_t* n_tiles_dev, int32_t n_tiles_cap, const float* oscale, const float* oshift, float* out,
+                       const float* residual, int32_t res_dim, int32_t mode, void* stream) {
+    return conv_fused_dispatch(true, layer, emb, perm, tb, idxB, strideB, tc, idxC, idxC2, strideC, w1img, inv_w1scale, w2img,
+                               inv_wscale, node_in, gather_idx, sh, sh_stride, seg_ptr, tile_node, n_tiles_dev, n_tiles_cap, oscale,
+                               oshift, out, residual, res_dim, mode, stream);
 }
 
 /* profiling aid (not part of the public header): pass 1 of dp_edge_mlp_tc alone */

@@ -7,6 +7,7 @@ hand-written sm_100a kernel reached through the C ABI (include/diffphore_b200.h)
     sampling_phore (one step)               /root/reference/src/utils/sampling.py:204-255
 """
 import math
+import os
 from types import SimpleNamespace
 
 import numpy as np
@@ -62,6 +63,10 @@ class ConvWeights:
                 img, s112 = _make_w2img112(_f32(w3).cpu(), _f32(sd[prefix + '.fc.3.bias']).cpu())
                 assert s112 == self.inv_wscale
                 self.w2img112 = img.to(device)
+                if os.environ.get('DIFFPHORE_W2', 'paths') == 'flat':     # EXPERIMENTAL (dp_conv_fused_flat), not the default
+                    img, sflat = _make_w2imgflat(_f32(w3).cpu(), _f32(sd[prefix + '.fc.3.bias']).cpu())
+                    assert sflat == self.inv_wscale
+                    self.w2imgflat = img.to(device)
                 img, self.inv_w1scale = _make_w1img(_f32(sd[prefix + '.fc.0.weight']).cpu(), _f32(sd[prefix + '.fc.0.bias']).cpu())
                 self.w1img = img.to(device)
         # eval BatchNorm (e3nn.nn.BatchNorm) and path weights folded into per-component scale/shift
@@ -119,6 +124,25 @@ def _make_w2img112(w3, b3):
     x = torch.zeros(nch, 112, 64, dtype=torch.float32)
     x[:, :100, :60] = w3.reshape(nch, 100, 60)
     x[:, :100, 60] = b3.reshape(nch, 100)
+    m = float(x.abs().max())
+    k = 12 - math.floor(math.log2(m)) if m > 0 and math.isfinite(m) else 0
+    xs = x * (2.0 ** k)
+    hi = xs.half()
+    lo = (xs - hi.float()).half()
+    img = torch.stack([hi, lo], 1).reshape(nch, 2, 14, 8, 8, 8).permute(0, 1, 4, 2, 3, 5)     # [c][h][kc][ng][r][j]
+    return img.contiguous().reshape(-1).view(torch.uint8), 2.0 ** (-k)
+
+
+def _make_w2imgflat(w3, b3):
+    """EXPERIMENTAL layout for dp_conv_fused_flat: like _make_w2img112, but the W columns are cut into consecutive 112-column
+    chunks regardless of the path boundaries (zero padding in the last chunk only): [ceil(W/112)][hi|lo][k/8][14][8][8] fp16.
+    Same power-of-two scale as _make_w2img112 (the maximum is the same).  Returns (uint8 image tensor, 2^-k)."""
+    W = w3.shape[0]
+    nch = (W + 111) // 112
+    x = torch.zeros(nch * 112, 64, dtype=torch.float32)
+    x[:W, :60] = w3
+    x[:W, 60] = b3
+    x = x.reshape(nch, 112, 64)
     m = float(x.abs().max())
     k = 12 - math.floor(math.log2(m)) if m > 0 and math.isfinite(m) else 0
     xs = x * (2.0 ** k)
@@ -586,8 +610,10 @@ class Engine:
             e0 = tm.start()
         if self.use_fused and tiles is not None and cw.w2img112 is not None:
             tile_node, n_tiles_dev, n_tiles_cap = tiles
-            L.check(self.lib.dp_conv_fused(cw.layer_id, p(emb), p(perm), p(tb), p(idxB), tb.shape[1], p(tc), p(idxC), p(idxC2),
-                                           tc.shape[1], p(cw.w1img), cw.inv_w1scale, p(cw.w2img112), cw.inv_wscale, p(node_in),
+            flat = getattr(cw, 'w2imgflat', None)                      # EXPERIMENTAL weight layout (DIFFPHORE_W2=flat)
+            fn = self.lib.dp_conv_fused if flat is None else self.lib.dp_conv_fused_flat
+            L.check(fn(cw.layer_id, p(emb), p(perm), p(tb), p(idxB), tb.shape[1], p(tc), p(idxC), p(idxC2),
+                                           tc.shape[1], p(cw.w1img), cw.inv_w1scale, p(cw.w2img112 if flat is None else flat), cw.inv_wscale, p(node_in),
                                            p(gather), p(sh), sh_stride, p(seg), p(tile_node), p(n_tiles_dev), n_tiles_cap,
                                            p(cw.oscale), p(cw.oshift), p(out), p(residual), res_dim, mode, st), 'dp_conv_fused')
             if tm is not None:

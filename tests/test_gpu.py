@@ -276,21 +276,22 @@ def _conv_case(layer, degs, seed=0, shift=0, n_in=700):
     return t
 
 
-def _run_conv_fused(layer, t, lib, mode=0, residual=None, out0=None):
-    from diffphore_b200.engine import _make_w1img, _make_w2img112, greedy_tiles
+def _run_conv_fused(layer, t, lib, mode=0, residual=None, out0=None, flat=False):
+    from diffphore_b200.engine import _make_w1img, _make_w2img112, _make_w2imgflat, greedy_tiles
     L, p, dev = lib, lib.ptr, torch.device('cuda:0')
     d_in, d_out, W, shs = _CF[layer]
     seg = torch.from_numpy(np.concatenate([[0], np.cumsum(t['degs'])]).astype(np.int32)).to(dev)
     tiles = greedy_tiles(t['degs'])
     tile_node = torch.tensor(tiles + [len(t['degs'])], dtype=torch.int32, device=dev)
     img1, inv1 = _make_w1img(t['w1'], t['b1'])
-    img2, inv2 = _make_w2img112(t['w3'], t['b3'])
+    img2, inv2 = (_make_w2imgflat if flat else _make_w2img112)(t['w3'], t['b3'])
     d = {k: v.to(dev) for k, v in t.items() if torch.is_tensor(v)}
     img1, img2 = img1.to(dev), img2.to(dev)
     out = torch.zeros(len(t['degs']), d_out, device=dev) if out0 is None else out0.clone().to(dev)
     res = None if residual is None else residual.to(dev)
     st = torch.cuda.current_stream().cuda_stream
-    L.check(L.load().dp_conv_fused(layer, p(d['emb']), None, p(d['tb']), p(d['ib']), 100, p(d['tb']), p(d['ic']), None, 100, p(img1),
+    fn = L.load().dp_conv_fused_flat if flat else L.load().dp_conv_fused
+    L.check(fn(layer, p(d['emb']), None, p(d['tb']), p(d['ib']), 100, p(d['tb']), p(d['ic']), None, 100, p(img1),
                                    inv1, p(img2), inv2, p(d['nodes']), p(d['gat']), p(d['sh']), shs, p(seg), p(tile_node), None,
                                    len(tiles), p(d['oscale']), p(d['oshift']), p(out), p(res), 0 if res is None else res.shape[1],
                                    mode, st), 'dp_conv_fused')
@@ -537,3 +538,15 @@ def test_forward_matches_the_committed_frozen_oracle_outputs(shape):
         for key, val in (('tr', tr), ('rot', rot), ('tor', tor[:b.n_rot])):
             ref = gold[f'{shape}_{tag}{key}']
             assert rel(val.cpu(), ref) <= 1e-4, (shape, tag, key, rel(val.cpu(), ref))
+
+
+@pytest.mark.skipif(os.environ.get('DIFFPHORE_TEST_FLAT') != '1', reason='experimental flat weight layout (dp_conv_fused_flat): '
+                    'set DIFFPHORE_TEST_FLAT=1; not yet validated on hardware (round-2 item, DESIGN.md section 8)')
+@pytest.mark.parametrize('layer', [0, 1, 2, 3, 5])
+def test_conv_fused_flat_layout_is_bit_identical_to_the_path_aligned_layout(built_lib, layer):
+    """dp_conv_fused_flat cuts the weight columns into 112-column chunks regardless of the path boundaries (9 % fewer MMA groups at
+    W = 2200); products and accumulation order are unchanged, so the outputs must equal dp_conv_fused bit for bit."""
+    rng = np.random.default_rng(layer)
+    degs = np.concatenate([rng.integers(0, 40, 150), [128, 0, 1, 127, 3, 256, 100, 79, 79, 79, 200, 5]])
+    t = _conv_case(layer, degs, seed=layer)
+    assert torch.equal(_run_conv_fused(layer, t, built_lib, flat=True), _run_conv_fused(layer, t, built_lib))

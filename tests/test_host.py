@@ -202,6 +202,23 @@ def test_fused_operand_images_reconstruct_the_weights():
     assert np.log2(inv) == round(np.log2(inv))                                  # exact power-of-two scale
 
 
+def test_flat_weight_image_reconstructs_the_weights():
+    """engine._make_w2imgflat (experimental layout of dp_conv_fused_flat): chunk c, column n of the image = weight column 112 c + n,
+    zero beyond W; same power-of-two scale as the path-aligned image."""
+    from diffphore_b200.engine import _make_w2imgflat, _make_w2img112
+    g = torch.Generator().manual_seed(0)
+    for W in (600, 1100, 1600, 2200):
+        w3, b3 = torch.randn(W, 60, generator=g) / 8, torch.randn(W, generator=g)
+        img, inv = _make_w2imgflat(w3, b3)
+        nch = (W + 111) // 112
+        h = img.view(torch.float16).reshape(nch, 2, 8, 14, 8, 8)                 # [c][hi|lo][k/8][n/8][n%8][k%8]
+        x = (h[:, 0].double() + h[:, 1].double()).permute(0, 2, 3, 1, 4).reshape(nch * 112, 64) * inv
+        assert float((x[:W, :60] - w3).abs().max()) < 2e-6 * float(w3.abs().max())
+        assert float((x[:W, 60] - b3).abs().max()) < 2e-6 * float(b3.abs().max())
+        assert float(x[W:].abs().max()) == 0 and float(x[:, 61:].abs().max()) == 0
+        assert inv == _make_w2img112(w3, b3)[1] and img.numel() == nch * 28672
+
+
 def test_packed_batch_expands_samples_like_a_naive_replication():
     """PackedBatch uploads per-pair arrays and expands the samples on the device; compare with collating deep copies."""
     from diffphore_b200.engine import ModelWeights, PackedBatch
