@@ -1,0 +1,18 @@
+#!/bin/bash
+# Round-2 A/B of the experimental flat weight layout (dp_conv_fused_flat) on a GPU box:
+#   gpurun --timeout 900 -- 'bash tools/ab_flat.sh'
+# 1. kernel-level bit-identity against the default layout, 2. the whole -m gpu suite on the flat path,
+# 3. bench.py with both layouts back to back (same box, same clocks).
+set -x
+mkdir -p gpurun_out
+DIFFPHORE_TEST_FLAT=1 timeout 120 python -m pytest tests/test_gpu.py -m gpu -x -q -k flat_layout 2>&1 | tail -3
+DIFFPHORE_W2=flat timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ab_default.json 2> gpurun_out/ab_default.err
+DIFFPHORE_W2=flat timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ab_flat.json 2> gpurun_out/ab_flat.err
+python - <<'PY'
+import json
+for tag in ('default', 'flat'):
+    d = json.loads(open(f'gpurun_out/ab_{tag}.json').read())
+    k = d['kernels']
+    print(tag, round(d['value'], 1), 'samples/s; e2e', round(d['e2e']['value'], 1), '; lig3', round(k['conv_fused:lig3']['ms_per_launch'], 3), 'ms; clocks', d['clocks']['sm_mhz'])
+PY
