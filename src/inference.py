@@ -142,7 +142,7 @@ class PoseSink:
         self.pending = []
 
     def submit(self, g, poses, run_time):
-        self.pending.append(self.pool.submit(self.process, g, poses, run_time))
+        self.pending.append((g.name, self.pool.submit(self.process, g, poses, run_time)))
 
     def process(self, g, poses, run_time):
         args, name, N = self.args, g.name, len(poses)
@@ -168,8 +168,15 @@ class PoseSink:
         return name, scores, run_time
 
     def drain(self):
-        """Results of everything submitted so far, in submission order."""
-        done, self.pending = [f.result() for f in self.pending], []
+        """Results of everything submitted so far, in submission order.  A pair whose output / scoring step raised (disk full,
+        unreadable template, ...) is reported and skipped like any other failing pair; it does not take the job down."""
+        done = []
+        for name, f in self.pending:
+            try:
+                done.append(f.result())
+            except Exception as e:
+                print(f'[W] Error occured when writing / scoring the poses of {name}, skipped. {e}')
+        self.pending = []
         return done
 
     def close(self):
@@ -247,7 +254,7 @@ def fit(args, model, complex_graphs, device, t_to_sigma, tmp_log='', n_report=10
         n_done += len(job)
         if tmp_log and n_done // n_report != (n_done - len(job)) // n_report:
             print(f'[I] {n_done}/{len(todo)} processed...')
-            part = [done[k] for k in done] + [r for r in (f.result() for f in sink.pending if f.done())]
+            part = [done[k] for k in done] + [f.result() for _, f in sink.pending if f.done() and f.exception() is None]
             json.dump({'name': [r[0] for r in part], 'fitscore': [r[1] for r in part], 'run_time': [r[2] for r in part],
                        'batch': n_done, 'total_time': time.time() - std_time}, open(tmp_log, 'w'), indent=4)
     for r in sink.drain():

@@ -174,6 +174,15 @@ def test_scoring_failure_sentinel_and_job_plan(gold, tmp_path, capsys):
     sink.close()
     assert scores == [-2.0] * 3 and 'set as -2.0' in capsys.readouterr().out       # inference.py:235-237
     assert not os.path.exists(tmp_path / 'run' / 'ranked_poses' / 'a__b_ranked.sdf')
+    # a pair whose output step raises is reported and skipped, the others still come back
+    sink = inference.PoseSink(args, workers=1)
+    bad = HeteroGraph()
+    bad.name, bad.phore_file, bad.sdf_template = 'x__bad', g.phore_file, None
+    sink.submit(bad, gold['kat_poses'][:2], 1.0)
+    sink.submit(g, gold['kat_poses'][:2], 1.0)
+    res = sink.drain()
+    sink.close()
+    assert [r[0] for r in res] == ['a__b'] and 'x__bad, skipped' in capsys.readouterr().out
     jobs = inference.plan_jobs(list(range(1000)), 40, pairs_cap=10 ** 6)
     assert [len(j) for j in jobs][:2] == [103, 103] and sum(len(j) for j in jobs) == 1000 and jobs[-1][-1] == 999
     assert [len(j) for j in inference.plan_jobs(list(range(7)), 40, pairs_cap=3)] == [3, 3, 1]
