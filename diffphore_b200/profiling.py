@@ -5,6 +5,8 @@ Algorithmic flops of one dp_edge_mlp launch:                 2*E*(in*hid + (hid+
 Algorithmic flops of one dp_conv_fused launch:               E*(2*(in+1)*hid + 2*(hid+1)*W + tp_flops)   (MLP + channel mixing;
     the tensor pipe executes 3 * 112/100 times the first term: 2-way FP16 split, chunks padded 100 -> 112 columns)
 """
+import os
+
 import torch
 
 
@@ -63,7 +65,10 @@ class KernelTimer:
             for kind, name, sec, E, m in self._resolved():
                 if kind == 'conv_fused' and select(name):
                     f += float(E) * (2.0 * (m['in_dim'] + 1) * m['hid'] + 2.0 * (m['hid'] + 1) * m['W'] + m['tp_flops'])
-                    mma += float(E) * 2.0 * 64 * (m['W'] * 1.12 + 64) * 3
+                    # columns the tensor pipe really multiplies per edge: W/100 chunks of 112 (path-aligned layout) or
+                    # ceil(W/112) chunks of 112 (experimental flat layout, DIFFPHORE_W2=flat)
+                    cols = -(-m['W'] // 112) * 112 if os.environ.get('DIFFPHORE_W2', 'paths') == 'flat' else m['W'] * 1.12
+                    mma += float(E) * 2.0 * 64 * (cols + 64) * 3
                     b += float(E) * (4 * m['W'] + 4 * m['d_in'] + 4 * 9 + 8) + m['n_out'] * 4 * m['d_out']
                     s += sec
                     n += 1
