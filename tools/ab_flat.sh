@@ -7,6 +7,8 @@ set -x
 mkdir -p gpurun_out
 DIFFPHORE_TEST_FLAT=1 timeout 120 python -m pytest tests/test_gpu.py -m gpu -x -q -k flat_layout 2>&1 | tail -3
 DIFFPHORE_W2=flat timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 100 python tools/conv_fused_probe.py 2>&1 | tail -8
+DIFFPHORE_W2=flat timeout 100 python tools/conv_fused_probe.py 2>&1 | tail -8
 timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ab_default.json 2> gpurun_out/ab_default.err
 DIFFPHORE_W2=flat timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ab_flat.json 2> gpurun_out/ab_flat.err
 python - <<'PY'
