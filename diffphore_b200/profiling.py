@@ -76,7 +76,8 @@ class KernelTimer:
                 return None
             return dict(achieved=f / s / 1e12, peak=peak_tflops, unit='TFLOP/s', frac=f / s / 1e12 / peak_tflops, launches=n,
                         flops_per_launch=f / n, ms_per_launch=1e3 * s / n, issued_mma_tflops=mma / s / 1e12,
-                        issued_mma_frac=mma / s / 1e12 / peak_tflops, equiv_hbm_gbs=b / s / 1e9, equiv_hbm_frac=b / s / 1e9 / hbm_gbs)
+                        issued_mma_frac=mma / s / 1e12 / peak_tflops, fp32_parity_bound_frac=f / mma,
+                        equiv_hbm_gbs=b / s / 1e9, equiv_hbm_frac=b / s / 1e9 / hbm_gbs)
         dom, allk = agg(lambda nm: nm == dominant), agg(lambda nm: True)
         if dom is None:
             return None
@@ -85,7 +86,7 @@ class KernelTimer:
         out.update(traffic=traffic_bytes, peak_source=f'{peak_src} dense bf16 cuBLAS throughput (sustained)', all_layers=allk,
                    note='achieved = algorithmic FLOPs E*(2*61*60 + 2*61*W + tp_flops) (both MLP layers + channel mixing) / CUDA-event '
                         'time; the fp32-parity FP16 split issues 3 MMAs per product and pads 100-column chunks to N=112 '
-                        '(issued_mma_*); equiv_hbm_* = bytes the unfused dp_tp_scatter would stream (SURVEY 8d) / this '
+                        '(issued_mma_*; fp32_parity_bound_frac = algorithmic / issued FLOPs = the largest `frac` this fp32-parity scheme can reach); equiv_hbm_* = bytes the unfused dp_tp_scatter would stream (SURVEY 8d) / this '
                         'kernel\'s time; traffic = dram__bytes_read.sum + dram__bytes_write.sum of this launch in '
                         'profiles/ncu_conv_fused_r1_final.csv')
         return out
