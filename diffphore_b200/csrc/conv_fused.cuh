@@ -63,6 +63,16 @@ template <class Base>
 struct CfFlat : Base {
     static constexpr bool FLAT = true;
 };
+// ... and with the last chunk's MMA N trimmed to its valid columns rounded up to 16 (1600 columns: 14 x 112 + 32 instead of 15 x 112)
+template <class Base>
+struct CfFlatTrim : Base {
+    static constexpr bool FLAT = true;
+    static constexpr bool TRIM = true;
+};
+template <class Cfg, class = void>
+struct cf_is_trim { static constexpr bool value = false; };
+template <class Cfg>
+struct cf_is_trim<Cfg, std::enable_if_t<Cfg::TRIM>> { static constexpr bool value = true; };
 template <class Cfg, class = void>
 struct cf_is_flat { static constexpr bool value = false; };
 template <class Cfg>
@@ -375,6 +385,8 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
     constexpr bool FLAT = cf_is_flat<Cfg>::value;
     constexpr int NCH = FLAT ? (Cfg::W + CF_N - 1) / CF_N : Cfg::W / CF_CHUNK;
     static_assert(FLAT || Cfg::W % CF_CHUNK == 0, "W must be a multiple of the chunk");
+    constexpr bool TRIM = cf_is_trim<Cfg>::value;                        // flat layout only: last chunk with a narrower MMA
+    constexpr int N_LAST = TRIM ? ((Cfg::W - (NCH - 1) * CF_N + 15) / 16) * 16 : CF_N;
     extern __shared__ __align__(1024) uint8_t cf_smem_raw[];
     uint8_t* b_st = cf_smem_raw;                                                    // STAGES x (hi | lo)
     uint8_t* alo = b_st + S::STAGES * CF_B_STAGE;                                   // 2 tiles x [k/8][m/8][m%8][k%8] fp16 (A lo)
@@ -444,6 +456,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
             const uint32_t a_hi_t = tmem_base + CF_A_COL + (uint32_t)(t * 32);
             const uint32_t a_lo_s = tc_smem(alo) + (uint32_t)(t * CF_ALO_TILE);
             const uint32_t idesc1 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // first layer: N = 64
+            const uint32_t idesc_last = (1u << 4) | ((uint32_t)(N_LAST >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             uint32_t g = 0, use = 0;                                        // use: items issued by this warp so far
             for (int pi = 0; pi < my_pairs; ++pi) {
                 constexpr bool mine = true;                             // (both MMA tiles of a pair tile always run; rows beyond its edges are zero)
@@ -505,6 +518,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
                     const uint32_t b_hi_s = b_base + s * CF_B_STAGE, b_lo_s = b_hi_s + CF_B_HALF;
                     const uint32_t slot = 2 * (use & 1) + (uint32_t)t;
                     const uint32_t d = tmem_base + slot * CF_SLOT_COLS;
+                    const uint32_t idc = (TRIM && c == NCH - 1) ? idesc_last : idesc;
 #pragma unroll
                     for (int combo = 0; combo < 3; ++combo) {              // hi*hi + hi*lo (A from TMEM) + lo*hi (A from smem)
                         const uint32_t bs = combo == 1 ? b_lo_s : b_hi_s;
@@ -513,8 +527,8 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
                             // fp16 K-major no-swizzle: core matrix = 8 rows x 8 halfs (128 B); B: 14 row groups per K chunk,
                             // A lo: 16 row groups per K chunk
                             const uint64_t bd = tc_smem_desc(bs + ks * 2 * (CF_N * 16), CF_N * 16, 128);
-                            if (combo < 2) cf_mma_f16_ts(d, a_hi_t + (uint32_t)(ks * 8), bd, idesc, (combo | ks) ? 1u : 0u);
-                            else cf_mma_f16_ss(d, tc_smem_desc(a_lo_s + ks * 2 * 2048, 2048, 128), bd, idesc, 1u);
+                            if (combo < 2) cf_mma_f16_ts(d, a_hi_t + (uint32_t)(ks * 8), bd, idc, (combo | ks) ? 1u : 0u);
+                            else cf_mma_f16_ss(d, tc_smem_desc(a_lo_s + ks * 2 * 2048, 2048, 128), bd, idc, 1u);
                         }
                     }
                     cf_commit(&t_full[slot]);

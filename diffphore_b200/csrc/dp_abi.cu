@@ -167,6 +167,19 @@ static int conv_fused_dispatch(bool flat, int32_t layer, const float* emb, const
     a.n_tiles = n_tiles_cap; a.oscale = oscale; a.oshift = oshift; a.out = out; a.residual = residual; a.res_dim = res_dim;
     a.mode = mode;
     a.dbg = g_cf_dbg_host;
+    if (flat && (mode & 16)) {                                            /* flat layout, last chunk's MMA trimmed (experimental) */
+        a.dbg = nullptr;
+        a.mode = mode & 15;
+        switch (layer) {
+            case DP_TP_L0: return conv_fused_launch<CfFlatTrim<TpL0>>(a, ST(stream));
+            case DP_TP_L1: return conv_fused_launch<CfFlatTrim<TpL1>>(a, ST(stream));
+            case DP_TP_L2: return conv_fused_launch<CfFlatTrim<TpL2>>(a, ST(stream));
+            case DP_TP_L3: return conv_fused_launch<CfFlatTrim<TpL3>>(a, ST(stream));
+            case DP_TP_TOR: return conv_fused_launch<CfFlatTrim<TpTor>>(a, ST(stream));
+        }
+        dp_set_error("dp_conv_fused_flat: unsupported layer %d", layer);
+        return DP_ERR_ARG;
+    }
     if (flat) {
         a.dbg = nullptr;
         switch (layer) {

@@ -63,10 +63,12 @@ class ConvWeights:
                 img, s112 = _make_w2img112(_f32(w3).cpu(), _f32(sd[prefix + '.fc.3.bias']).cpu())
                 assert s112 == self.inv_wscale
                 self.w2img112 = img.to(device)
-                if os.environ.get('DIFFPHORE_W2', 'paths') == 'flat':     # EXPERIMENTAL (dp_conv_fused_flat), not the default
+                layout = os.environ.get('DIFFPHORE_W2', 'paths')
+                if layout in ('flat', 'flat_trim'):                       # EXPERIMENTAL (dp_conv_fused_flat), not the default
                     img, sflat = _make_w2imgflat(_f32(w3).cpu(), _f32(sd[prefix + '.fc.3.bias']).cpu())
                     assert sflat == self.inv_wscale
                     self.w2imgflat = img.to(device)
+                    self.flat_mode_bits = 16 if layout == 'flat_trim' else 0      # bit 4 of `mode`: last chunk's MMA trimmed
                 img, self.inv_w1scale = _make_w1img(_f32(sd[prefix + '.fc.0.weight']).cpu(), _f32(sd[prefix + '.fc.0.bias']).cpu())
                 self.w1img = img.to(device)
         # eval BatchNorm (e3nn.nn.BatchNorm) and path weights folded into per-component scale/shift
@@ -615,7 +617,8 @@ class Engine:
             L.check(fn(cw.layer_id, p(emb), p(perm), p(tb), p(idxB), tb.shape[1], p(tc), p(idxC), p(idxC2),
                                            tc.shape[1], p(cw.w1img), cw.inv_w1scale, p(cw.w2img112 if flat is None else flat), cw.inv_wscale, p(node_in),
                                            p(gather), p(sh), sh_stride, p(seg), p(tile_node), p(n_tiles_dev), n_tiles_cap,
-                                           p(cw.oscale), p(cw.oshift), p(out), p(residual), res_dim, mode, st), 'dp_conv_fused')
+                                           p(cw.oscale), p(cw.oshift), p(out), p(residual), res_dim,
+                                           mode if flat is None else mode | cw.flat_mode_bits, st), 'dp_conv_fused')
             if tm is not None:
                 tm.stop('conv_fused', name, e0, n_rec, dict(W=cw.W, hid=cw.hid, in_dim=cw.in_dim, d_in=cw.d_in, d_out=cw.d_out,
                                                             n_out=n_out, tp_flops=cw.tp_flops))

@@ -67,7 +67,8 @@ class KernelTimer:
                     f += float(E) * (2.0 * (m['in_dim'] + 1) * m['hid'] + 2.0 * (m['hid'] + 1) * m['W'] + m['tp_flops'])
                     # columns the tensor pipe really multiplies per edge: W/100 chunks of 112 (path-aligned layout) or
                     # ceil(W/112) chunks of 112 (experimental flat layout, DIFFPHORE_W2=flat)
-                    cols = -(-m['W'] // 112) * 112 if os.environ.get('DIFFPHORE_W2', 'paths') == 'flat' else m['W'] * 1.12
+                    layout = os.environ.get('DIFFPHORE_W2', 'paths')
+                    cols = {'flat': -(-m['W'] // 112) * 112, 'flat_trim': -(-m['W'] // 16) * 16}.get(layout, m['W'] * 1.12)
                     mma += float(E) * 2.0 * 64 * (cols + 64) * 3
                     b += float(E) * (4 * m['W'] + 4 * m['d_in'] + 4 * 9 + 8) + m['n_out'] * 4 * m['d_out']
                     s += sec

@@ -276,7 +276,7 @@ def _conv_case(layer, degs, seed=0, shift=0, n_in=700):
     return t
 
 
-def _run_conv_fused(layer, t, lib, mode=0, residual=None, out0=None, flat=False):
+def _run_conv_fused(layer, t, lib, mode=0, residual=None, out0=None, flat=False, trim=False):
     from diffphore_b200.engine import _make_w1img, _make_w2img112, _make_w2imgflat, greedy_tiles
     L, p, dev = lib, lib.ptr, torch.device('cuda:0')
     d_in, d_out, W, shs = _CF[layer]
@@ -294,7 +294,7 @@ def _run_conv_fused(layer, t, lib, mode=0, residual=None, out0=None, flat=False)
     L.check(fn(layer, p(d['emb']), None, p(d['tb']), p(d['ib']), 100, p(d['tb']), p(d['ic']), None, 100, p(img1),
                                    inv1, p(img2), inv2, p(d['nodes']), p(d['gat']), p(d['sh']), shs, p(seg), p(tile_node), None,
                                    len(tiles), p(d['oscale']), p(d['oshift']), p(out), p(res), 0 if res is None else res.shape[1],
-                                   mode, st), 'dp_conv_fused')
+                                   mode | (16 if trim else 0), st), 'dp_conv_fused')
     torch.cuda.synchronize()
     return out.cpu()
 
@@ -549,4 +549,7 @@ def test_conv_fused_flat_layout_is_bit_identical_to_the_path_aligned_layout(buil
     rng = np.random.default_rng(layer)
     degs = np.concatenate([rng.integers(0, 40, 150), [128, 0, 1, 127, 3, 256, 100, 79, 79, 79, 200, 5]])
     t = _conv_case(layer, degs, seed=layer)
-    assert torch.equal(_run_conv_fused(layer, t, built_lib, flat=True), _run_conv_fused(layer, t, built_lib))
+    ref = _run_conv_fused(layer, t, built_lib)
+    assert torch.equal(_run_conv_fused(layer, t, built_lib, flat=True), ref)
+    # ... and with the last chunk's MMA trimmed to its valid columns (mode bit 4; added after the flat layout was validated)
+    assert torch.equal(_run_conv_fused(layer, t, built_lib, flat=True, trim=True), ref)

@@ -11,9 +11,11 @@ timeout 100 python tools/conv_fused_probe.py 2>&1 | tail -8
 DIFFPHORE_W2=flat timeout 100 python tools/conv_fused_probe.py 2>&1 | tail -8
 timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ab_default.json 2> gpurun_out/ab_default.err
 DIFFPHORE_W2=flat timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ab_flat.json 2> gpurun_out/ab_flat.err
+DIFFPHORE_W2=flat_trim timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+DIFFPHORE_W2=flat_trim timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ab_flat_trim.json 2> gpurun_out/ab_flat_trim.err
 python - <<'PY'
 import json
-for tag in ('default', 'flat'):
+for tag in ('default', 'flat', 'flat_trim'):
     d = json.loads(open(f'gpurun_out/ab_{tag}.json').read())
     k = d['kernels']
     print(tag, round(d['value'], 1), 'samples/s; e2e', round(d['e2e']['value'], 1), '; lig3', round(k['conv_fused:lig3']['ms_per_launch'], 3), 'ms; clocks', d['clocks']['sm_mhz'])
