@@ -845,7 +845,7 @@ static int conv_fused_launch(const ConvFusedArgs& a, cudaStream_t st) {
     }
     const int n_pairs = a.n_tiles;
     const int grid = n_pairs < n_sm ? n_pairs : n_sm;
-    if constexpr (Cfg::W == 2200) {
+    if constexpr (Cfg::W == 2200 && !cf_is_flat<Cfg>::value) {
         if (a.dbg) {                                                       // profiling aid (tools/conv_fused_probe.py --stamps)
             auto pk = conv_fused_kernel<Cfg, true>;
             cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
