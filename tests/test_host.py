@@ -239,3 +239,42 @@ def test_packed_batch_expands_samples_like_a_naive_replication():
         elif k not in ('h2d_bytes', 'S', 'device'):
             assert va == v, k
     assert a.tiles_cross_lig[2] > 0 and a.tiles_cross_lig[0].shape[0] == a.tiles_cross_lig[2] + 1
+
+
+@pytest.mark.parametrize('layout', ['paths', 'flat', 'flat_trim'])
+def test_engine_conv_dispatch_follows_the_weight_layout(monkeypatch, layout):
+    """Host glue of Engine._conv (no GPU: the library object is replaced by a recorder): the default layout calls dp_conv_fused
+    with the path-aligned image; DIFFPHORE_W2=flat / flat_trim (experimental) call dp_conv_fused_flat with the flat image and
+    mode bit 4 for the trimmed last chunk."""
+    from types import SimpleNamespace
+    from diffphore_b200.engine import ModelWeights, Engine
+    if layout == 'paths':
+        monkeypatch.delenv('DIFFPHORE_W2', raising=False)
+    else:
+        monkeypatch.setenv('DIFFPHORE_W2', layout)
+    w = ModelWeights(random_state_dict(0), 'cpu')
+    eng = Engine(w)
+    calls = []
+
+    def rec(name):
+        def f(*a):
+            calls.append((name, a))
+            return 0
+        return f
+    eng.lib = SimpleNamespace(dp_conv_fused=rec('dp_conv_fused'), dp_conv_fused_flat=rec('dp_conv_fused_flat'))
+    cw = w.convs[('lig', 3)]
+    assert (getattr(cw, 'w2imgflat', None) is None) == (layout == 'paths')
+    z = lambda *s: torch.zeros(*s)
+    zi = lambda *s: torch.zeros(*s, dtype=torch.int32)
+    ws = SimpleNamespace(n_launches=0)
+    tiles = (zi(2), None, 1)
+    eng._conv(cw, ws, z(4, 20), None, z(3, 100), zi(4), z(3, 100), zi(4), None, None, 4, z(3, 100), zi(4), z(4, 9), 9, zi(4),
+              z(3, 100), z(3, 100), 100, 1, 3, 0, 'lig3', tiles)
+    (name, a), = calls
+    assert ws.n_launches == 1
+    assert name == ('dp_conv_fused' if layout == 'paths' else 'dp_conv_fused_flat')
+    img = cw.w2img112 if layout == 'paths' else cw.w2imgflat
+    as_int = lambda v: v if isinstance(v, int) or v is None else v.value
+    assert as_int(a[12]) == img.data_ptr() and a[0] == cw.layer_id
+    assert a[27] == (1 | 16 if layout == 'flat_trim' else 1)                      # mode (+ trim bit)
+    assert img.numel() == (22 if layout == 'paths' else 20) * 28672
