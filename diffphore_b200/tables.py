@@ -65,13 +65,17 @@ class TorusScoreNorm:
         s = (s - np.log(SIGMA_MIN)) / (np.log(SIGMA_MAX) - np.log(SIGMA_MIN)) * SIGMA_N
         return np.round(np.clip(s, 0, SIGMA_N)).astype(int)
 
-    def _row(self, i):
+    def score_row(self, i):
+        """score_[i, :] = grad / p over the x grid with N = 100 images (torus.py:11-22,38-43); NaN where both underflow."""
         x, sig = self._x, self._sigma[i]
         k = np.arange(-100, 101)[:, None]
         xs = x[None] + 2 * np.pi * k
         e = np.exp(-xs ** 2 / 2 / sig ** 2)
         with np.errstate(invalid='ignore', divide='ignore'):
-            score_row = (xs / sig ** 2 * e).sum(0) / e.sum(0)
+            return (xs / sig ** 2 * e).sum(0) / e.sum(0)
+
+    def _row(self, i):
+        sig, score_row = self._sigma[i], self.score_row(i)
         rng = np.random.RandomState(self.seed * 100003 + i)
         s = sig * rng.randn(self.n_samples)
         s = (s + np.pi) % (2 * np.pi) - np.pi

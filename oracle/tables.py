@@ -61,9 +61,9 @@ def torus_sigma_index(sigma):
     return np.round(np.clip(s, 0, SIGMA_N)).astype(int)
 
 
-def torus_score_norm_row(idx, seed=0, n_samples=10000):
-    """score_norm_[idx] (torus.py:75-79): mean over 10000 samples x ~ wrapped N(0, sigma_idx) of score(x, sigma)^2,
-    with score from the nearest-grid table score_ = grad/p (N=100 images, torus.py:11-43,46-55)."""
+def torus_score_row(idx):
+    """score_[idx, :] = grad / p with N = 100 images (torus.py:11-22,38-43); pinned on the reference's own p / grad functions
+    (tests/golden/tables_ref.npz, tools/make_tables_golden.py)."""
     x = 10 ** np.linspace(np.log10(X_MIN), 0, TX_N + 1) * np.pi
     sig = (10 ** np.linspace(np.log10(SIGMA_MIN), np.log10(SIGMA_MAX), SIGMA_N + 1) * np.pi)[idx]
     p_ = 0
@@ -73,7 +73,14 @@ def torus_score_norm_row(idx, seed=0, n_samples=10000):
         p_ = p_ + e
         g_ = g_ + (x + 2 * np.pi * i) / sig ** 2 * e
     with np.errstate(invalid="ignore", divide="ignore"):
-        score_row = g_ / p_      # NaN where both underflow, exactly as the reference table
+        return g_ / p_           # NaN where both underflow, exactly as the reference table
+
+
+def torus_score_norm_row(idx, seed=0, n_samples=10000):
+    """score_norm_[idx] (torus.py:75-79): mean over 10000 samples x ~ wrapped N(0, sigma_idx) of score(x, sigma)^2,
+    with score from the nearest-grid table score_ = grad/p (N=100 images, torus.py:11-43,46-55)."""
+    sig = (10 ** np.linspace(np.log10(SIGMA_MIN), np.log10(SIGMA_MAX), SIGMA_N + 1) * np.pi)[idx]
+    score_row = torus_score_row(idx)
     rng = np.random.RandomState(seed * 100003 + idx)
     s = sig * rng.randn(n_samples)                                        # sample (torus.py:69-72)
     s = (s + np.pi) % (2 * np.pi) - np.pi

@@ -220,6 +220,35 @@ def test_tables_product_equals_oracle():
     assert So3ScoreNorm()(np.float32([0.001]))[0] == So3ScoreNorm()(np.float32([0.01]))[0]        # clipped index
 
 
+def test_score_norm_tables_equal_the_reference_functions():
+    """tests/golden/tables_ref.npz (tools/make_tables_golden.py): the table-building functions of the reference's so3.py /
+    torus.py, extracted unmodified and evaluated for the rows of the 20-step schedule.  so3: _exp_score_norms[idx]; torus: the
+    deterministic score_ = grad / p rows (the Monte-Carlo average on top is unseeded in the reference, H1: checked against the
+    exact second moment instead)."""
+    from oracle import tables as ot
+    from diffphore_b200 import tables as pt
+    gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'tables_ref.npz'))
+    assert np.array_equal(ot.so3_eps_index(gold['so3_eps']), gold['so3_idx'])
+    assert np.array_equal(pt.So3ScoreNorm.index(gold['so3_eps']), gold['so3_idx'])
+    assert np.allclose(So3ScoreNorm()(gold['so3_eps']), gold['so3_exp_score_norm'], rtol=1e-12)
+    assert np.allclose(pt.So3ScoreNorm()(gold['so3_eps']), gold['so3_exp_score_norm'], rtol=1e-9)
+    assert np.array_equal(ot.torus_sigma_index(gold['torus_sigma']), gold['torus_idx'])
+    assert np.array_equal(pt.TorusScoreNorm.index(gold['torus_sigma']), gold['torus_idx'])
+    prod = pt.TorusScoreNorm(seed=0)
+    for i, ref_row in zip(gold['torus_idx'], gold['torus_score_rows']):
+        assert np.allclose(ot.torus_score_row(int(i))[::25], ref_row, rtol=1e-12, equal_nan=True)
+        assert np.allclose(prod.score_row(int(i))[::25], ref_row, rtol=1e-9, equal_nan=True)
+    # the seeded Monte-Carlo rows agree with the exact E[score^2] of the nearest-grid score table under the wrapped normal
+    for i in gold['torus_idx'][[0, 9, 19]]:
+        sig = (10 ** np.linspace(np.log10(ot.SIGMA_MIN), np.log10(ot.SIGMA_MAX), ot.SIGMA_N + 1) * np.pi)[int(i)]
+        rng = np.random.RandomState(12345)
+        s = sig * rng.randn(400000)
+        s = (s + np.pi) % (2 * np.pi) - np.pi
+        xi = (np.log(np.abs(s) / np.pi) - np.log(ot.X_MIN)) / (0 - np.log(ot.X_MIN)) * ot.TX_N
+        exact = float((ot.torus_score_row(int(i))[np.round(np.clip(xi, 0, ot.TX_N)).astype(int)] ** 2).mean())
+        assert abs(ot.torus_score_norm_row(int(i), 0) / exact - 1) < 0.05, (i, exact)
+
+
 def test_conformer_update_oracle_properties():
     """modify_conformer keeps bond lengths and (by the Kabsch re-alignment) the centroid displacement equal to tr."""
     g = _noised(load_pairs('synthetic', 1, 14, 5), 1, 0.5, 3)[0]
