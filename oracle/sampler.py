@@ -1,6 +1,8 @@
 """ORACLE (test infrastructure, not product code).
 
-CPU restatement of the reverse-diffusion driver and the per-sample conformer update, bug-for-bug:
+CPU restatement of the reverse-diffusion driver and the per-sample conformer update, bug-for-bug; PINNED on the reference's own
+code: tests/golden/ref_sampler.npz holds outputs of the unmodified reference modules run over shims (tools/make_sampler_golden.py),
+tests/test_oracle.py compares every function below with them.
 
     randomize_position                 /root/reference/src/utils/sampling.py:16-63
     sampling_phore                     /root/reference/src/utils/sampling.py:174-255

@@ -249,6 +249,76 @@ def test_score_norm_tables_equal_the_reference_functions():
         assert abs(ot.torus_score_norm_row(int(i), 0) / exact - 1) < 0.05, (i, exact)
 
 
+def _sampler_gold_graphs():
+    """The start graphs of tools/make_sampler_golden.py: 2 synthetic pairs + the first real-shaped pair, 2 copies each."""
+    graphs = load_pairs('synthetic', 2, 14, 5) + load_pairs('real', 1)
+    return [g.clone() for g in graphs for _ in range(2)]
+
+
+def test_sampler_oracle_equals_the_reference_sampler_code():
+    """tests/golden/ref_sampler.npz (tools/make_sampler_golden.py): outputs of the UNMODIFIED reference utils/sampling.py,
+    diffusion_utils.py, torsion.py, geometry.py run over shims on seeded inputs.  Pins randomize_position (with its draws replayed),
+    modify_conformer with / without torsion updates (Kabsch, H4 norm-point quirk, skipped bonds), the t schedule, t_to_sigma and
+    the sinusoidal embedding of the oracle AND of the product's host code."""
+    from diffphore_b200 import sampler as psamp
+    from diffphore_b200.engine import ModelWeights
+    from oracle.model import sinusoidal_embedding
+    gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'ref_sampler.npz'))
+    sched = osamp.get_t_schedule(20)
+    assert np.array_equal(sched, gold['t_schedule']) and np.array_equal(psamp.get_t_schedule(20), gold['t_schedule'])
+    w = ModelWeights(random_state_dict(0), 'cpu')
+    for t, ref_sig, ref_emb in zip(sched, gold['t_to_sigma'], gold['sigma_emb']):
+        assert np.allclose(w.t_to_sigma(t), ref_sig, rtol=2e-7)          # (model side: fp32, like the tensors of set_time_phore)
+        assert np.allclose(sinusoidal_embedding(10000 * torch.tensor([float(t)]), 20)[0].numpy(), ref_emb, atol=1e-6)
+        assert np.allclose(w.step_consts(float(t), So3ScoreNorm(), TorusScoreNorm(seed=0))[0:20].numpy(), ref_emb, atol=1e-6)
+    # randomize_position with the reference's draws
+    dl = _sampler_gold_graphs()
+    n_rot = [int(g['ligand'].edge_mask.sum()) for g in dl]
+    offs = np.concatenate([[0], np.cumsum(n_rot)])
+    osamp.randomize_position(dl, False, False, 5.0, [gold['rand_tor'][offs[i]:offs[i + 1]] for i in range(len(dl))],
+                             list(gold['rand_rot']), list(gold['rand_tr']))
+    assert float((torch.cat([g['ligand'].pos for g in dl]) - torch.from_numpy(gold['rand_pos'])).abs().max()) <= 2e-5
+    assert float((torch.cat([g['ligand'].norm for g in dl]) - torch.from_numpy(gold['rand_norm'])).abs().max()) <= 2e-5
+    # modify_conformer, with torsions (some skipped) and rigid only, starting from the reference's randomised poses
+    ptr = np.concatenate([[0], np.cumsum([g['ligand'].pos.shape[0] for g in dl])])
+    for i, g in enumerate(dl):
+        g['ligand'].pos = torch.from_numpy(gold['rand_pos'][ptr[i]:ptr[i + 1]]).clone()
+        g['ligand'].norm = torch.from_numpy(gold['rand_norm'][ptr[i]:ptr[i + 1]]).clone()
+        trp, rotp = torch.from_numpy(gold['upd_tr'][i:i + 1]), torch.from_numpy(gold['upd_rot'][i])
+        a = osamp.modify_conformer(g.clone(), trp, rotp, gold['upd_tor'][offs[i]:offs[i + 1]])
+        b = osamp.modify_conformer(g.clone(), trp, rotp, None)
+        for got, key in ((a['ligand'].pos, 'upd_pos'), (a['ligand'].norm, 'upd_norm'), (b['ligand'].pos, 'rigid_pos'),
+                         (b['ligand'].norm, 'rigid_norm')):
+            assert float((got - torch.from_numpy(gold[key][ptr[i]:ptr[i + 1]])).abs().max()) <= 2e-5, (i, key)
+
+
+@needs_ckpt
+def test_oracle_sampling_loop_equals_the_reference_sampling_phore():
+    """sampling_phore of the reference (sampling.py:174-280) driving the UNMODIFIED reference model with the shipped checkpoint for
+    6 steps (no_random and ode variants, tests/golden/ref_sampler.npz) against oracle.sampler.sampling + OracleScoreModel."""
+    from oracle.model import default_config
+    gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'ref_sampler.npz'))
+    base = load_pairs('real', 1)[0]
+    n = base['ligand'].pos.shape[0]
+    start = []
+    for k in range(3):
+        g = base.clone()
+        g['ligand'].pos = torch.from_numpy(gold['samp_start_pos'][k * n:(k + 1) * n]).clone()
+        g['ligand'].norm = torch.from_numpy(gold['samp_start_norm'][k * n:(k + 1) * n]).clone()
+        start.append(g)
+    om = OracleScoreModel(real_state_dict(), So3ScoreNorm(), TorusScoreNorm(seed=0))
+    steps = int(gold['samp_steps'])
+    for tag, kw in (('norandom', {}), ('ode', dict(ode=True))):
+        res = osamp.sampling([g.clone() for g in start], om, steps, default_config(), collate, batch_size=3, noise=None, **kw)
+        pos = torch.cat([g['ligand'].pos for g in res])
+        ref = torch.from_numpy(gold[f'samp_{tag}_pos'])
+        rmsd = [float(((pos[k * n:(k + 1) * n] - ref[k * n:(k + 1) * n]) ** 2).sum(1).mean().sqrt()) for k in range(3)]
+        assert max(rmsd) <= 1e-4, (tag, rmsd)
+        # samples 0 and 2 started from the same pose: the reference's own batched run separates them by a few 1e-6 A
+        assert float((ref[:n] - ref[2 * n:]).abs().max()) <= 2e-5
+        print(tag, 'RMSD oracle vs reference sampling_phore:', rmsd)
+
+
 def test_conformer_update_oracle_properties():
     """modify_conformer keeps bond lengths and (by the Kabsch re-alignment) the centroid displacement equal to tr."""
     g = _noised(load_pairs('synthetic', 1, 14, 5), 1, 0.5, 3)[0]
