@@ -115,7 +115,7 @@ def build_graph(record):
     return g
 
 
-def get_perfect_similarity(g, weights=(1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.0),
+def get_perfect_similarity(g, weights=(1.0, 1.0, 1.0, 1.0, 1.0, 0.0, 1.0, 1.0, 1.0, 1.0, 0.0),      # HY and EX do not count
                            alpha=(1.0, 1.0, 0.7, 1.0, 1.0, 0.7, 1.0, 1.0, 0.7, 1.0, 0.837)):
     """Type/count-only pharmacophore fingerprint similarity used by --min_similarity (inference.py:273-312)."""
     phore_volume = g['phore'].phoretype.sum(dim=0)

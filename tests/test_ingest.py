@@ -189,8 +189,13 @@ def test_scoring_failure_sentinel_and_job_plan(gold, tmp_path, capsys):
     assert [len(j) for j in inference.plan_jobs(list(range(3)), 10 ** 5, pairs_cap=8)] == [1, 1, 1]
 
 
-def test_perfect_similarity_matches_the_reference_formula():
+def test_perfect_similarity_matches_the_reference_formula(gold):
     import inference
+    for pt, lp, ref in zip(gold['sim_phore_types'], gold['sim_lig_ph'], gold['sim_values']):      # the reference's own function
+        gg = HeteroGraph()
+        gg['phore'].phoretype = torch.nn.functional.one_hot(torch.from_numpy(pt), 11).float()
+        gg['ligand'].ph = torch.from_numpy(lp)
+        assert abs(inference.get_perfect_similarity(gg) - ref) <= 1e-6 * max(1.0, abs(ref))
     g = HeteroGraph()
     g['phore'].phoretype = torch.nn.functional.one_hot(torch.tensor([0, 1, 1, 4, 10, 10]), 11).float()
     g['ligand'].ph = torch.tensor([1., 1, 0, 0, 3, 0, 0, 0, 0, 0, 0])

@@ -132,6 +132,24 @@ def main():
         if l.startswith('>  <fitscore>'):
             fits.append(R[i + 1])
     out['ranked_names'], out['ranked_fitscore_text'], out['ranked_first_atom'] = np.asarray(rnames), np.asarray(fits), np.asarray(first)
+    # ---- get_perfect_similarity (inference.py:273-312), extracted unmodified from the reference's inference.py
+    import ast
+    src = open(os.path.join(REF, 'src/inference.py')).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == 'get_perfect_similarity'][0]
+    ns = {'torch': torch}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), 'inference.py', 'exec'), ns)
+    rng = np.random.RandomState(5)
+    ptypes = rng.randint(0, 11, size=(6, 9))
+    ligph = rng.randint(0, 4, size=(6, 11)).astype(np.float32)
+    ptypes[5] = 10                                                         # only exclusion spheres: weighted volume 0 -> -1
+    sims = []
+    for pt, lp in zip(ptypes, ligph):
+        gg = HeteroGraph()
+        gg['phore'].phoretype = torch.nn.functional.one_hot(torch.from_numpy(pt), 11).float()
+        gg['ligand'].ph = torch.from_numpy(lp)
+        gg.name = 'x'
+        sims.append(ns['get_perfect_similarity'](gg))
+    out['sim_phore_types'], out['sim_lig_ph'], out['sim_values'] = ptypes, ligph, np.asarray(sims, dtype=np.float64)
     path = os.path.join(ROOT, 'tests/golden/ingest.npz')
     np.savez_compressed(path, **out)
     print('wrote', path, os.path.getsize(path), 'bytes;', len(names), 'ligands,', out['kat_poses'].shape, 'poses')
