@@ -74,21 +74,28 @@ def parse_args(argv=None):
 
 
 def read_input(phore_ligand_csv=None, phore=None, ligand=None):
-    """Records {phore, ligand_description} from a csv (columns ligand_description, phore) or a single / listed pair."""
+    """Records {phore, ligand_description} (inference.py:99-137): rows of a csv with the columns `phore` and `ligand_description`
+    (duplicates dropped), or the product of the pharmacophore(s) and ligand(s) given on the command line - a directory stands
+    for every file in it, a `.smi` file for its lines."""
     records = []
-    if phore_ligand_csv is not None:
-        import csv
-        with open(phore_ligand_csv) as fh:
-            for row in csv.DictReader(fh):
-                records.append({'phore': row['phore'], 'ligand_description': row['ligand_description']})
-    elif phore is not None and ligand is not None:
-        def expand(x):
-            if os.path.isfile(x) and not x.endswith(('.sdf', '.mol', '.mol2', '.phore')):
-                return [l.strip() for l in open(x) if l.strip()]
-            return [x]
-        for ph in expand(phore):
-            for lg in expand(ligand):
-                records.append({'phore': ph, 'ligand_description': lg})
+    if phore_ligand_csv is not None and os.path.exists(phore_ligand_csv):
+        import pandas as pd
+        records = pd.read_csv(phore_ligand_csv).drop_duplicates().to_dict('records')
+    else:
+        phore_list, ligand_list = [], []
+        if phore is not None and ligand is not None and os.path.exists(phore):
+            if os.path.isdir(phore):
+                phore_list = [os.path.join(phore, f) for f in os.listdir(phore)]
+            elif os.path.isfile(phore):
+                phore_list = [phore]
+            if os.path.exists(ligand):
+                if os.path.isdir(ligand):
+                    ligand_list = [os.path.join(ligand, f) for f in os.listdir(ligand)]
+                elif ligand.endswith('.smi'):
+                    ligand_list = [line.strip() for line in open(ligand).readlines()]
+                else:
+                    ligand_list = [ligand]
+        records = [{'phore': p, 'ligand_description': l} for p in phore_list for l in ligand_list]
     if not records:
         raise ValueError('Invalid input. Either phore_ligand_csv or protein and ligand must be specified')
     return records

@@ -264,3 +264,31 @@ def test_fit_host_logic_jobs_error_isolation_resume_and_keep_update(gold, tmp_pa
         m2 = inference.fit(args, model, graphs, 'cpu', None)
         assert _FakeSampler.jobs == [[names[2]]] and m2['name'] == names
         assert [m2['fitscore'][i] for i in (0, 1, 3, 4)] == m['fitscore']
+
+
+def test_read_input_equals_the_reference_function(gold, tmp_path):
+    """inference.read_input against the reference's own function (inference.py:99-137, run by tools/make_ingest_golden.py on the
+    same directory tree): csv with a duplicated row, single pair, directories of pharmacophores / ligands, a .smi file."""
+    import json
+    import inference
+    root = str(tmp_path)
+    os.makedirs(os.path.join(root, 'phores')); os.makedirs(os.path.join(root, 'ligs'))
+    for f in ('a.phore', 'b.phore'):
+        open(os.path.join(root, 'phores', f), 'w').write('x')
+    for f in ('l1.sdf', 'l2.sdf', 'l3.sdf'):
+        open(os.path.join(root, 'ligs', f), 'w').write('x')
+    open(os.path.join(root, 'lig.smi'), 'w').write('CCO\nc1ccccc1\n')
+    open(os.path.join(root, 'task.csv'), 'w').write('ligand_description,phore\nligs/l1.sdf,phores/a.phore\nligs/l2.sdf,phores/a.phore\n'
+                                                    'ligs/l1.sdf,phores/a.phore\n')
+    cases = {'csv': (os.path.join(root, 'task.csv'), None, None),
+             'single': (None, os.path.join(root, 'phores/a.phore'), os.path.join(root, 'ligs/l1.sdf')),
+             'dirs': (None, os.path.join(root, 'phores'), os.path.join(root, 'ligs')),
+             'smi': (None, os.path.join(root, 'phores/b.phore'), os.path.join(root, 'lig.smi'))}
+    ref = json.loads(str(gold['read_input_json']))
+    for k, a in cases.items():
+        recs = inference.read_input(*a)
+        got = sorted([r['phore'].replace(root, '<ROOT>'), r['ligand_description'].replace(root, '<ROOT>')] for r in recs)
+        assert got == ref[k], k
+    assert len(ref['csv']) == 2 and len(ref['dirs']) == 6 and len(ref['smi']) == 2
+    with pytest.raises(ValueError, match='Invalid input'):
+        inference.read_input(None, os.path.join(root, 'missing.phore'), os.path.join(root, 'ligs'))

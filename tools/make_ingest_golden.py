@@ -150,6 +150,29 @@ def main():
         gg.name = 'x'
         sims.append(ns['get_perfect_similarity'](gg))
     out['sim_phore_types'], out['sim_lig_ph'], out['sim_values'] = ptypes, ligph, np.asarray(sims, dtype=np.float64)
+    # ---- read_input (inference.py:99-137), extracted unmodified, on a small directory tree (rebuilt by the test)
+    import json, tempfile, pandas
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == 'read_input'][0]
+    ns = {'os': os, 'pd': pandas}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), 'inference.py', 'exec'), ns)
+    root = tempfile.mkdtemp()
+    os.makedirs(os.path.join(root, 'phores')); os.makedirs(os.path.join(root, 'ligs'))
+    for f in ('a.phore', 'b.phore'):
+        open(os.path.join(root, 'phores', f), 'w').write('x')
+    for f in ('l1.sdf', 'l2.sdf', 'l3.sdf'):
+        open(os.path.join(root, 'ligs', f), 'w').write('x')
+    open(os.path.join(root, 'lig.smi'), 'w').write('CCO\nc1ccccc1\n')
+    open(os.path.join(root, 'task.csv'), 'w').write('ligand_description,phore\nligs/l1.sdf,phores/a.phore\nligs/l2.sdf,phores/a.phore\n'
+                                                    'ligs/l1.sdf,phores/a.phore\n')
+    cases = {'csv': (os.path.join(root, 'task.csv'), None, None),
+             'single': (None, os.path.join(root, 'phores/a.phore'), os.path.join(root, 'ligs/l1.sdf')),
+             'dirs': (None, os.path.join(root, 'phores'), os.path.join(root, 'ligs')),
+             'smi': (None, os.path.join(root, 'phores/b.phore'), os.path.join(root, 'lig.smi'))}
+    res = {}
+    for k, a in cases.items():
+        recs = ns['read_input'](*a)
+        res[k] = sorted([r['phore'].replace(root, '<ROOT>'), r['ligand_description'].replace(root, '<ROOT>')] for r in recs)
+    out['read_input_json'] = np.asarray(json.dumps(res))
     path = os.path.join(ROOT, 'tests/golden/ingest.npz')
     np.savez_compressed(path, **out)
     print('wrote', path, os.path.getsize(path), 'bytes;', len(names), 'ligands,', out['kat_poses'].shape, 'poses')
