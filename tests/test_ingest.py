@@ -292,3 +292,37 @@ def test_read_input_equals_the_reference_function(gold, tmp_path):
     assert len(ref['csv']) == 2 and len(ref['dirs']) == 6 and len(ref['smi']) == 2
     with pytest.raises(ValueError, match='Invalid input'):
         inference.read_input(None, os.path.join(root, 'missing.phore'), os.path.join(root, 'ligs'))
+
+
+def test_get_model_kwarg_mapping_equals_the_reference_function(gold, monkeypatch):
+    """utils.utils.get_model against the reference's own get_model (utils/utils.py:113-168, run by tools/make_ingest_golden.py with
+    a recording constructor on the shipped model_parameters.yml): every constructor kwarg the mirror derives from the Namespace has
+    the reference's value, the reference-only kwargs are accepted by the mirrored model class, and the embedding spec is the same."""
+    import json
+    import yaml
+    from argparse import Namespace
+    from utils import utils as uu
+    ref = json.loads(str(gold['get_model_kwargs_json']))
+    args = Namespace(**yaml.full_load(str(gold['model_parameters_yml'])))
+    args.no_torsion = False
+    captured, emb = {}, {}
+
+    class Recorder:
+        def __init__(self, **kw):
+            captured.update(kw)
+
+        def to(self, device):
+            return self
+    monkeypatch.setattr(uu, 'PhoreModel', Recorder)
+    monkeypatch.setattr(uu, 'get_timestep_embedding', lambda *a, **kw: emb.update(args=a, kw=kw) or 'emb')
+    uu.get_model(args, torch.device('cpu'), t_to_sigma=None, no_parallel=True)
+    mine = {k: v for k, v in captured.items() if k not in ('t_to_sigma', 'device', 'timestep_emb_func')}
+    assert set(mine) <= set(ref), set(mine) - set(ref)
+    assert all(mine[k] == ref[k] for k in mine), {k: (mine[k], ref[k]) for k in mine if mine[k] != ref[k]}
+    spec = json.loads(str(gold['get_model_emb_json']))
+    got = list(emb['args']) + [emb['kw'][k] for k in ('embedding_type', 'embedding_dim', 'embedding_scale') if k in emb['kw']]
+    assert got == [spec['embedding_type'], spec['embedding_dim'], spec['embedding_scale']]
+    # the kwargs only the reference passes select features outside the shipped flag set; the mirrored class takes them all
+    from models.score_model_phore import TensorProductScoreModel
+    model = TensorProductScoreModel(t_to_sigma=None, device=torch.device('cpu'), timestep_emb_func=None, **ref)
+    assert len(model.state_dict()) == 385

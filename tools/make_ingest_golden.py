@@ -173,6 +173,29 @@ def main():
         recs = ns['read_input'](*a)
         res[k] = sorted([r['phore'].replace(root, '<ROOT>'), r['ligand_description'].replace(root, '<ROOT>')] for r in recs)
     out['read_input_json'] = np.asarray(json.dumps(res))
+    # ---- get_model (utils/utils.py:113-168), extracted unmodified: constructor kwargs it derives from the shipped model_parameters.yml
+    import yaml
+    from argparse import Namespace
+    usrc = open(os.path.join(REF, 'src/utils/utils.py')).read()
+    fn = [n for n in ast.parse(usrc).body if isinstance(n, ast.FunctionDef) and n.name == 'get_model'][0]
+    captured = {}
+
+    class _Recorder:
+        def __init__(self, **kw):
+            captured.update(kw)
+
+        def to(self, device):
+            return self
+    ns = {'PhoreModel': _Recorder, 'get_timestep_embedding': lambda **kw: ('emb', kw), 'torch': torch,
+          'DataParallel': lambda m: m}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), 'utils.py', 'exec'), ns)
+    margs = Namespace(**yaml.full_load(open(os.path.join(REF, 'weights/diffphore_calibrated_warmuped_ft/model_parameters.yml'))))
+    margs.no_torsion = False
+    ns['get_model'](margs, torch.device('cpu'), t_to_sigma=None, no_parallel=True)
+    kw = {k: v for k, v in captured.items() if k not in ('t_to_sigma', 'device', 'timestep_emb_func')}
+    out['get_model_kwargs_json'] = np.asarray(json.dumps(kw, sort_keys=True))
+    out['get_model_emb_json'] = np.asarray(json.dumps(captured['timestep_emb_func'][1], sort_keys=True))
+    out['model_parameters_yml'] = np.asarray(open(os.path.join(REF, 'weights/diffphore_calibrated_warmuped_ft/model_parameters.yml')).read())
     path = os.path.join(ROOT, 'tests/golden/ingest.npz')
     np.savez_compressed(path, **out)
     print('wrote', path, os.path.getsize(path), 'bytes;', len(names), 'ligands,', out['kat_poses'].shape, 'poses')
