@@ -271,6 +271,15 @@ def test_sampler_oracle_equals_the_reference_sampler_code():
         assert np.allclose(w.t_to_sigma(t), ref_sig, rtol=2e-7)          # (model side: fp32, like the tensors of set_time_phore)
         assert np.allclose(sinusoidal_embedding(10000 * torch.tensor([float(t)]), 20)[0].numpy(), ref_emb, atol=1e-6)
         assert np.allclose(w.step_consts(float(t), So3ScoreNorm(), TorusScoreNorm(seed=0))[0:20].numpy(), ref_emb, atol=1e-6)
+    # the mirrored host helpers of src/utils/diffusion_utils.py
+    from types import SimpleNamespace
+    from utils import diffusion_utils as mdu
+    margs = SimpleNamespace(tr_sigma_min=0.1, tr_sigma_max=5.0, rot_sigma_min=0.1, rot_sigma_max=1.5, tor_sigma_min=0.0314,
+                            tor_sigma_max=3.14)
+    emb = mdu.get_timestep_embedding('sinusoidal', 20, 10000)
+    assert np.array_equal(mdu.get_t_schedule(20), gold['t_schedule'])
+    assert np.array_equal(np.asarray([mdu.t_to_sigma(t, t, t, margs) for t in sched]), gold['t_to_sigma'])
+    assert np.array_equal(torch.stack([emb(torch.tensor([float(t)])) for t in sched]).squeeze(1).numpy(), gold['sigma_emb'])
     # randomize_position with the reference's draws
     dl = _sampler_gold_graphs()
     n_rot = [int(g['ligand'].edge_mask.sum()) for g in dl]
