@@ -326,3 +326,17 @@ def test_get_model_kwarg_mapping_equals_the_reference_function(gold, monkeypatch
     from models.score_model_phore import TensorProductScoreModel
     model = TensorProductScoreModel(t_to_sigma=None, device=torch.device('cpu'), timestep_emb_func=None, **ref)
     assert len(model.state_dict()) == 385
+
+
+def test_cli_flags_and_defaults_equal_the_reference_parser(gold):
+    """inference.parse_args against the reference's own parser (inference.py:54-96): same flags, same defaults (except --model_dir,
+    which defaults to the shipped weights directory here), same str2bool / target_fishing handling; two new optional flags."""
+    import json
+    import inference
+    ref = json.loads(str(gold['parse_args_defaults_json']))
+    mine = vars(inference.parse_args([]))
+    assert set(ref) <= set(mine) and set(mine) - set(ref) == {'seed', 'pairs_per_job'}
+    assert {k for k in ref if ref[k] != mine[k]} == {'model_dir'}
+    ref = json.loads(str(gold['parse_args_flags_json']))
+    mine = vars(inference.parse_args(['--target_fishing', 'true', '--no_random', '--ode', '--overwrite', 'yes', '--cutoff', '0.4']))
+    assert {k for k in ref if ref[k] != mine[k]} == {'model_dir'} and mine['fitness'] == ref['fitness']

@@ -196,6 +196,17 @@ def main():
     out['get_model_kwargs_json'] = np.asarray(json.dumps(kw, sort_keys=True))
     out['get_model_emb_json'] = np.asarray(json.dumps(captured['timestep_emb_func'][1], sort_keys=True))
     out['model_parameters_yml'] = np.asarray(open(os.path.join(REF, 'weights/diffphore_calibrated_warmuped_ft/model_parameters.yml')).read())
+    # ---- parse_args (inference.py:54-96), extracted unmodified: flag names and defaults of the CLI
+    from argparse import ArgumentParser, FileType
+    fns = {n.name: n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef)}
+    ns = {'ArgumentParser': ArgumentParser, 'FileType': FileType, 'Namespace': Namespace, 'sys': sys, 'os': os}
+    for nm in ('str2bool', 'parse_args'):
+        exec(compile(ast.Module(body=[fns[nm]], type_ignores=[]), 'inference.py', 'exec'), ns)
+    argv, sys.argv = sys.argv, ['inference.py']
+    out['parse_args_defaults_json'] = np.asarray(json.dumps(vars(ns['parse_args']()), sort_keys=True))
+    sys.argv = ['inference.py', '--target_fishing', 'true', '--no_random', '--ode', '--overwrite', 'yes', '--cutoff', '0.4']
+    out['parse_args_flags_json'] = np.asarray(json.dumps(vars(ns['parse_args']()), sort_keys=True))
+    sys.argv = argv
     path = os.path.join(ROOT, 'tests/golden/ingest.npz')
     np.savez_compressed(path, **out)
     print('wrote', path, os.path.getsize(path), 'bytes;', len(names), 'ligands,', out['kat_poses'].shape, 'poses')
