@@ -553,3 +553,63 @@ def test_conv_fused_flat_layout_is_bit_identical_to_the_path_aligned_layout(buil
     assert torch.equal(_run_conv_fused(layer, t, built_lib, flat=True), ref)
     # ... and with the last chunk's MMA trimmed to its valid columns (mode bit 4; added after the flat layout was validated)
     assert torch.equal(_run_conv_fused(layer, t, built_lib, flat=True, trim=True), ref)
+
+
+refgold = pytest.mark.skipif(os.environ.get('DIFFPHORE_TEST_REFGOLD') != '1', reason='direct CUDA-vs-reference-output tests, written '
+                             'after the round-1 GPU budget ran out: enable with DIFFPHORE_TEST_REFGOLD=1 once run on a GPU box '
+                             '(the same parity holds transitively today: CUDA = oracle on the GPU, oracle = reference outputs on CPU)')
+
+
+@refgold
+@needs_ckpt
+def test_forward_matches_the_reference_model_outputs_directly():
+    """CUDA forward against tests/golden/ref_forward.npz, the outputs of the UNMODIFIED reference TensorProductScoreModel (shipped
+    checkpoint, run over shims by tools/make_golden.py) - no oracle in between.  rel-L2 <= 1e-4 (real-shaped pairs)."""
+    from diffphore_b200.engine import ModelWeights, Engine
+    from diffphore_b200.graph import graph_from_arrays
+    from diffphore_b200.tables import So3ScoreNorm, TorusScoreNorm
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    z = np.load(os.path.join(root, 'tests/golden/ref_forward.npz'))
+    a = np.load(os.path.join(root, 'tests/golden/real_pairs.npz'))
+    graphs = [graph_from_arrays(a, f'p{k}_') for k in (11, 0, 5)]
+    S, t = int(z['real_S']), float(z['real_t'])
+    dl, o = [g.clone() for g in graphs for _ in range(S)], 0
+    for g in dl:
+        n = g['ligand'].pos.shape[0]
+        g['ligand'].pos = torch.from_numpy(z['real_pos'][o:o + n].copy())
+        g['ligand'].norm = torch.from_numpy(z['real_norm'][o:o + n].copy())
+        o += n
+    dev = torch.device('cuda:0')
+    w = ModelWeights(real_state_dict(), dev)
+    eng = Engine(w)
+    b, ws = eng.pack(dl, 1)
+    tr, rot, tor = eng.forward(b, ws, w.step_consts(t, So3ScoreNorm(), TorusScoreNorm(seed=0), dt=0.05).to(dev))
+    torch.cuda.synchronize()
+    for key, val in (('tr', tr), ('rot', rot), ('tor', tor)):
+        assert rel(val.cpu(), z[f'real_{key}']) <= 1e-4, (key, rel(val.cpu(), z[f'real_{key}']))
+
+
+@refgold
+@needs_ckpt
+@pytest.mark.parametrize('mode', ['norandom', 'ode'])
+def test_trajectory_matches_the_reference_sampling_phore_directly(mode):
+    """CUDA denoising loop against tests/golden/ref_sampler.npz: final coordinates of the reference's own sampling_phore
+    (sampling.py:174-280) driving the unmodified reference model for 6 steps (no_random / ode), RMSD <= 1e-4 A per sample."""
+    from diffphore_b200.engine import ModelWeights
+    from diffphore_b200.sampler import DenoisingSampler
+    from diffphore_b200.tables import So3ScoreNorm, TorusScoreNorm
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gold = np.load(os.path.join(root, 'tests/golden/ref_sampler.npz'))
+    base = load_pairs('real', 1)[0]
+    n = base['ligand'].pos.shape[0]
+    start = []
+    for k in range(3):
+        g = base.clone()
+        g['ligand'].pos = torch.from_numpy(gold['samp_start_pos'][k * n:(k + 1) * n]).clone()
+        g['ligand'].norm = torch.from_numpy(gold['samp_start_norm'][k * n:(k + 1) * n]).clone()
+        start.append(g)
+    smp = DenoisingSampler(ModelWeights(real_state_dict(), torch.device('cuda:0')), int(gold['samp_steps']), So3ScoreNorm(),
+                           TorusScoreNorm(seed=0), ode=(mode == 'ode'))
+    pos, ptr = smp.run(start, 1, no_random=True, randomize=False)          # every start graph is its own "pair", poses as given
+    ref = torch.from_numpy(gold[f'samp_{mode}_pos'])
+    assert max(_rmsd(pos, ref, ptr)) <= 1e-4, _rmsd(pos, ref, ptr)
