@@ -73,29 +73,27 @@ def parse_args(argv=None):
     return args
 
 
+def _expand(path, smi_lines=False):
+    """A directory stands for every entry in it, a `.smi` file (ligand side only) for its lines, anything else for itself."""
+    if os.path.isdir(path):
+        return [os.path.join(path, name) for name in os.listdir(path)]
+    if smi_lines and path.endswith('.smi'):
+        with open(path) as fh:
+            return [line.strip() for line in fh]
+    return [path]
+
+
 def read_input(phore_ligand_csv=None, phore=None, ligand=None):
-    """Records {phore, ligand_description} (inference.py:99-137): rows of a csv with the columns `phore` and `ligand_description`
-    (duplicates dropped), or the product of the pharmacophore(s) and ligand(s) given on the command line - a directory stands
-    for every file in it, a `.smi` file for its lines."""
-    records = []
+    """Records {phore, ligand_description} with the input rules of the reference (inference.py:99-137; outputs pinned on its own
+    function in tests/test_ingest.py): an existing csv with the columns `phore` / `ligand_description` wins (duplicate rows
+    dropped); otherwise the product of the pharmacophores and ligands named on the command line, provided both paths exist."""
     if phore_ligand_csv is not None and os.path.exists(phore_ligand_csv):
         import pandas as pd
         records = pd.read_csv(phore_ligand_csv).drop_duplicates().to_dict('records')
+    elif phore is not None and ligand is not None and os.path.exists(phore) and os.path.exists(ligand):
+        records = [{'phore': ph, 'ligand_description': lg} for ph in _expand(phore) for lg in _expand(ligand, smi_lines=True)]
     else:
-        phore_list, ligand_list = [], []
-        if phore is not None and ligand is not None and os.path.exists(phore):
-            if os.path.isdir(phore):
-                phore_list = [os.path.join(phore, f) for f in os.listdir(phore)]
-            elif os.path.isfile(phore):
-                phore_list = [phore]
-            if os.path.exists(ligand):
-                if os.path.isdir(ligand):
-                    ligand_list = [os.path.join(ligand, f) for f in os.listdir(ligand)]
-                elif ligand.endswith('.smi'):
-                    ligand_list = [line.strip() for line in open(ligand).readlines()]
-                else:
-                    ligand_list = [ligand]
-        records = [{'phore': p, 'ligand_description': l} for p in phore_list for l in ligand_list]
+        records = []
     if not records:
         raise ValueError('Invalid input. Either phore_ligand_csv or protein and ligand must be specified')
     return records
