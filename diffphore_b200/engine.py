@@ -63,8 +63,10 @@ class ConvWeights:
                 img, s112 = _make_w2img112(_f32(w3).cpu(), _f32(sd[prefix + '.fc.3.bias']).cpu())
                 assert s112 == self.inv_wscale
                 self.w2img112 = img.to(device)
-                layout = os.environ.get('DIFFPHORE_W2', 'paths')
-                if layout in ('flat', 'flat_trim'):                       # EXPERIMENTAL (dp_conv_fused_flat), not the default
+                # weight-column layout of dp_conv_fused: 'flat_trim' (default: consecutive 112-column chunks, last MMA trimmed;
+                # measured +3.3 % on the cfg2 step, profiles/ab_flat_r2.txt), 'flat', or 'paths' (100-column path-aligned chunks)
+                layout = os.environ.get('DIFFPHORE_W2', 'flat_trim')
+                if layout in ('flat', 'flat_trim'):
                     img, sflat = _make_w2imgflat(_f32(w3).cpu(), _f32(sd[prefix + '.fc.3.bias']).cpu())
                     assert sflat == self.inv_wscale
                     self.w2imgflat = img.to(device)

@@ -247,6 +247,15 @@ class OracleScoreModel:
         d1, d2 = curr_angle - a1, curr_angle - a2
         # torch.sort(...).indices[:,0] of [|d1|,|d2|]: index 0 unless |d2| < |d1| (stable on ties)
         norm_real = torch.where(d2.abs() < d1.abs(), d2, d1)
+        if getattr(self, 'branch_log', None) is not None:
+            # H7 diagnostics (tests only): the discrete decisions of this block per cross edge and their margins.  `active`:
+            # edges whose rotate_norm is not identically zero (some phore type agrees with the atom's fingerprint).
+            raw = torch.cross(lig_norm, pnorm[dst], dim=-1)
+            self.branch_log.append(dict(src=src.clone(), active=aggreement.sum(-1) != 0, clamped=raw < 1e-12,
+                                        choice=(d2.abs() < d1.abs()).squeeze(-1),
+                                        clamp_margin=(raw - 1e-12).abs(),
+                                        choice_margin=torch.where(a1 == a2, torch.full_like(d1, float('inf')),
+                                                                  (d2.abs() - d1.abs()).abs()).squeeze(-1)))
         rotate_norm = rotate_norm * norm_real
         self._rec('cross.edge_vec', edge_vec)
         self._rec('cross.rotate_norm', rotate_norm)

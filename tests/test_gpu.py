@@ -68,14 +68,87 @@ def test_trajectory_20_steps_random_weights():
     assert max(_rmsd(pos, ref, ptr)) <= 1e-4, _rmsd(pos, ref, ptr)
 
 
+def _branch_decisions(om, graphs_like, pos, norm):
+    """H7 decisions (component-wise clamp of smp:877, angle choice of smp:885) of the oracle's cross-graph block evaluated at a
+    given state (pos [n_lig,3], norm [n_lig,33] in data_list order)."""
+    from diffphore_b200.graph import collate
+    from oracle import sampler as osamp
+    dl, o = [g.clone() for g in graphs_like], 0
+    for g in dl:
+        n = g['ligand'].pos.shape[0]
+        g['ligand'].pos, g['ligand'].norm = pos[o:o + n].clone(), norm[o:o + n].clone()
+        o += n
+    b = collate(dl)
+    osamp.set_time(b, 0.5, len(dl))
+    om.branch_log = []
+    _cross_only(om, b)
+    d, om.branch_log = om.branch_log[0], None
+    return d, b['ligand'].batch
+
+
+def _cross_only(om, b):
+    # build_cross_conv_graph reads ligand.node_sigma_emb, which build_lig_conv_graph writes (smp:717)
+    om.build_lig_conv_graph(b)
+    om.build_cross_conv_graph(b)
+
+
+def _trajectory_with_branch_report(sd, graphs, S, steps, seed, near=1e-5):
+    """20-step trajectories of the oracle and of the CUDA path (eager launches) on identical draws, with the H7 report SURVEY 8d
+    asks for: per sample the number of cross edges whose discrete decisions (clamp sign per component, angle choice) differ
+    between the two trajectories at any step (`flips`) and the number whose decision margin is below `near` on either side
+    (`near_ties`: a decision the two fp32 evaluations may legitimately take differently)."""
+    from diffphore_b200.engine import ModelWeights
+    from diffphore_b200.sampler import DenoisingSampler
+    from diffphore_b200.graph import collate
+    from diffphore_b200.tables import So3ScoreNorm, TorusScoreNorm
+    from oracle.model import OracleScoreModel, default_config
+    from oracle import sampler as osamp
+    init, noise, n_rot = make_draws(graphs, S, seed, steps=steps)
+    so3n, torn = So3ScoreNorm(), TorusScoreNorm()
+    dl = oracle_initial_graphs(graphs, S, init, n_rot)
+    om = OracleScoreModel(sd, so3n, torn)
+    om.branch_log = []
+    ref = osamp.sampling(dl, om, steps, default_config(), collate, batch_size=len(dl), noise=noise)
+    o_log, om.branch_log = om.branch_log, None
+    ref_pos = torch.cat([g['ligand'].pos for g in ref])
+    dev = torch.device('cuda:0')
+    smp = DenoisingSampler(ModelWeights(sd, dev), steps, so3n, torn)
+    resident = smp.prepare(graphs, S)
+    smp.reset(resident, init=init)
+    (b, ws, _, _), = resident
+    B = b.B
+    flips, ties = np.zeros(B, int), np.zeros(B, int)
+    for k in range(steps):
+        c, batch = _branch_decisions(om, dl, b.pos.cpu(), b.norm.cpu())
+        o = o_log[k]
+        act = (o['active'] | c['active'])
+        diff = act & ((o['clamped'] != c['clamped']).any(1) | (o['choice'] != c['choice']))
+        tie = act & ((torch.minimum(o['clamp_margin'], c['clamp_margin']) < near).any(1) |
+                     (torch.minimum(o['choice_margin'], c['choice_margin']) < near))
+        g_of_edge = batch[o['src']]
+        flips += np.bincount(g_of_edge[diff].numpy(), minlength=B)
+        ties += np.bincount(g_of_edge[tie].numpy(), minlength=B)
+        z = tuple(torch.as_tensor(noise[k][key], dtype=torch.float32).contiguous().to(dev) for key in ('tr', 'rot', 'tor'))
+        smp.engine.forward(b, ws, smp.consts[k])
+        smp.engine.update(b, ws, smp.consts[k], *z)
+    torch.cuda.synchronize()
+    ptr = np.concatenate([[0], np.cumsum(b.n_per)])
+    return _rmsd(b.pos.cpu(), ref_pos, ptr), flips, ties
+
+
 @needs_ckpt
 def test_trajectory_20_steps_shipped_checkpoint():
-    """cfg1: reference example pair shapes, shipped weights, 4 samples, 20 steps, injected noise (H2) and tables (H1)."""
+    """cfg1: reference example pair shapes, shipped weights, 4 samples, 20 steps, injected noise (H2) and tables (H1).  Every
+    sample whose discrete H7 decisions agree with the oracle's along the whole trajectory must end within 1e-4 A RMSD; samples
+    with a flipped decision are reported ("report discrete-branch mismatch count") and bounded."""
     graphs = [load_pairs('real', 12)[11]]                                 # STK936575 x sQC pharmacophore
-    pos, ref, ptr = _trajectory(real_state_dict(), graphs, 4, 20, 5)
-    r = _rmsd(pos, ref, ptr)
-    assert np.median(r) <= 1e-4, r
-    assert max(r) <= 1e-2, r          # H7: a discrete branch flip (clamp / angle choice) may separate one sample
+    r, flips, ties = _trajectory_with_branch_report(real_state_dict(), graphs, 4, 20, 5)
+    print(f'cfg1 trajectory: RMSD {r}, H7 flips per sample {flips.tolist()}, near-ties per sample {ties.tolist()}')
+    for i in range(len(r)):
+        if flips[i] == 0 and ties[i] == 0:
+            assert r[i] <= 1e-4, (i, r, flips, ties)
+    assert np.median(r) <= 1e-4, (r, flips, ties)
+    assert max(r) <= 1e-2, (r, flips, ties)          # a flipped clamp / angle choice rescales one edge's SH: bounded, not chaotic
 
 
 def test_edge_cases_no_rotatable_bonds_and_neighbour_cap():
@@ -540,8 +613,6 @@ def test_forward_matches_the_committed_frozen_oracle_outputs(shape):
             assert rel(val.cpu(), ref) <= 1e-4, (shape, tag, key, rel(val.cpu(), ref))
 
 
-@pytest.mark.skipif(os.environ.get('DIFFPHORE_TEST_FLAT') != '1', reason='experimental flat weight layout (dp_conv_fused_flat): '
-                    'set DIFFPHORE_TEST_FLAT=1; not yet validated on hardware (round-2 item, DESIGN.md section 8)')
 @pytest.mark.parametrize('layer', [0, 1, 2, 3, 5])
 def test_conv_fused_flat_layout_is_bit_identical_to_the_path_aligned_layout(built_lib, layer):
     """dp_conv_fused_flat cuts the weight columns into 112-column chunks regardless of the path boundaries (9 % fewer MMA groups at
@@ -555,12 +626,6 @@ def test_conv_fused_flat_layout_is_bit_identical_to_the_path_aligned_layout(buil
     assert torch.equal(_run_conv_fused(layer, t, built_lib, flat=True, trim=True), ref)
 
 
-refgold = pytest.mark.skipif(os.environ.get('DIFFPHORE_TEST_REFGOLD') != '1', reason='direct CUDA-vs-reference-output tests, written '
-                             'after the round-1 GPU budget ran out: enable with DIFFPHORE_TEST_REFGOLD=1 once run on a GPU box '
-                             '(the same parity holds transitively today: CUDA = oracle on the GPU, oracle = reference outputs on CPU)')
-
-
-@refgold
 @needs_ckpt
 def test_forward_matches_the_reference_model_outputs_directly():
     """CUDA forward against tests/golden/ref_forward.npz, the outputs of the UNMODIFIED reference TensorProductScoreModel (shipped
@@ -589,7 +654,6 @@ def test_forward_matches_the_reference_model_outputs_directly():
         assert rel(val.cpu(), z[f'real_{key}']) <= 1e-4, (key, rel(val.cpu(), z[f'real_{key}']))
 
 
-@refgold
 @needs_ckpt
 @pytest.mark.parametrize('mode', ['norandom', 'ode'])
 def test_trajectory_matches_the_reference_sampling_phore_directly(mode):
@@ -615,10 +679,9 @@ def test_trajectory_matches_the_reference_sampling_phore_directly(mode):
     assert max(_rmsd(pos, ref, ptr)) <= 1e-4, _rmsd(pos, ref, ptr)
 
 
-@refgold
 def test_no_final_step_noise_matches_the_oracle():
     """--no_final_step_noise (sampling.py:230-244: zero noise in the last step only) against the oracle fed the same noise with
-    its last step zeroed.  (Gated with the other tests written after the round-1 GPU budget ran out.)"""
+    its last step zeroed."""
     from diffphore_b200.engine import ModelWeights
     from diffphore_b200.sampler import DenoisingSampler
     from diffphore_b200.graph import collate
