@@ -97,17 +97,21 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def cpu_reference_rate(n_pairs, samples, threads, steps=INF_STEPS):
+def cpu_reference_rate(n_pairs, samples, threads, steps=INF_STEPS, first_pair=0, forward_only=False, real=False):
     """Oracle = reference op graph on CPU (materialised per-edge TP weights, index_add scatter, per-step re-collation,
-    per-sample scipy/LAPACK conformer update), batch_size = samples like the reference batches within a pair."""
-    from tests.parity_util import random_state_dict, load_pairs, make_draws, oracle_initial_graphs
+    per-sample scipy/LAPACK conformer update); batch_size = min(samples, 40): the reference batches the copies of ONE pair,
+    `sample_per_complex` = 40 at a time (sampling.py:210, inference.py:184).  forward_only: the model calls alone (same
+    batches, same count) without noise / conformer update.  real: the cfg1 pair (STK936575 x the 79-node example pharmacophore).
+    Returns (samples/s, seconds)."""
+    from tests.parity_util import make_draws, oracle_initial_graphs
+    from diffphore_b200.synthetic import random_state_dict, make_pairs, real_example_pairs
     from diffphore_b200.graph import collate
     from oracle.model import OracleScoreModel, default_config
     from oracle import sampler as osamp
     from oracle.tables import So3ScoreNorm, TorusScoreNorm
     torch.set_num_threads(threads)
     sd = random_state_dict(0)
-    graphs = load_pairs('synthetic', n_pairs, N_ATOMS, N_PHORE)
+    graphs = [real_example_pairs(12)[11]] if real else make_pairs(n_pairs, N_ATOMS, N_PHORE, first=first_pair)
     init, noise, n_rot = make_draws(graphs, samples, 0, steps=steps)
     dl = oracle_initial_graphs(graphs, samples, init, n_rot)
     so3n, torn = So3ScoreNorm(), TorusScoreNorm()
@@ -116,10 +120,36 @@ def cpu_reference_rate(n_pairs, samples, threads, steps=INF_STEPS):
         s = np.asarray([0.1 ** (1 - t) * 1.5 ** t], dtype=np.float32)
         so3n(s)
         torn(np.asarray([0.0314 ** (1 - t) * 3.14 ** t], dtype=np.float32))
+    bs = min(samples, 40)
     t0 = time.time()
-    osamp.sampling(dl, om, steps, default_config(), collate, batch_size=samples, noise=noise)
+    if forward_only:
+        for t in osamp.get_t_schedule(steps):
+            for k in range(0, len(dl), bs):
+                batch = collate(dl[k:k + bs])
+                osamp.set_time(batch, float(t), batch.num_graphs)
+                with torch.no_grad():
+                    om(batch)
+    else:
+        osamp.sampling(dl, om, steps, default_config(), collate, batch_size=bs, noise=noise)
     dt = time.time() - t0
     return len(dl) / dt, dt
+
+
+REF_PAIRS_PER_STEP = 1                                          # x 40 samples x 20 steps at batch 40: ~10-25 s of CPU work per bench step
+
+
+def cpu_baseline_block(cores):
+    """cpu_baseline of the main arm: the oracle port on `cores` threads, bounded samples of the cfg2 workload at the reference's
+    batching (40 copies of one pair per batch), full step and forward only, plus the cfg1 job."""
+    r, dt = cpu_reference_rate(REF_PAIRS_PER_STEP, SAMPLES, cores)
+    rf, dtf = cpu_reference_rate(1, SAMPLES, cores, forward_only=True)
+    r1, dt1 = cpu_reference_rate(1, 4, cores, real=True)
+    return {'value': r, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+            'sample': f'{REF_PAIRS_PER_STEP} pairs x {SAMPLES} samples x {INF_STEPS} steps of the cfg2 shape at batch {SAMPLES} ({dt:.1f} s of CPU work, '
+                      f'oracle port, torch.set_num_threads({cores})); extrapolates linearly in pairs',
+            'forward_only': {'value': rf, 'unit': 'samples/s', 'sample': f'1 pair x {SAMPLES} samples x {INF_STEPS} model calls at batch {SAMPLES} ({dtf:.1f} s)'},
+            'cfg1': {'value': r1, 'unit': 'samples/s', 'seconds': dt1,
+                     'sample': 'STK936575 x sQC pharmacophore (N=20, P=79), 4 samples x 20 steps at batch 4, random-init weights'}}
 
 
 def main():
@@ -136,6 +166,7 @@ def main():
                                                         '(reference example ligands x the 79-node example pharmacophore), shipped checkpoint if present')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip the non-headline cfg3 / cfg4 / cfg5 lines')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -146,15 +177,16 @@ def main():
         if rank != 0:
             return
         vals = []
-        n_pairs, samples = 8, 8                                  # ~12 s of CPU work per bench step
         for _ in range(args.warmup if args.warmup < 2 else 1):
             cpu_reference_rate(1, 2, cores, steps=2)
         t0 = time.time()
-        for _ in range(args.steps):
-            r, dt = cpu_reference_rate(n_pairs, samples, cores)
+        for k in range(args.steps):                              # every bench step denoises the NEXT pairs of the cfg2 workload
+            r, dt = cpu_reference_rate(REF_PAIRS_PER_STEP, SAMPLES, cores, first_pair=(k * REF_PAIRS_PER_STEP) % N_PAIRS)
             vals.append(r)
         v = float(np.mean(vals))
-        sample = f'{n_pairs} pair x {samples} samples x {INF_STEPS} steps of the cfg2 shape per bench step (oracle port of the reference CPU path)'
+        sample = (f'{REF_PAIRS_PER_STEP} pairs x {SAMPLES} samples x {INF_STEPS} steps of the cfg2 shape per bench step at batch {SAMPLES} '
+                  f'(the reference batches the {SAMPLES} copies of one pair, sampling.py:210); {args.steps * REF_PAIRS_PER_STEP} distinct pairs over the run; '
+                  'oracle port of the reference CPU path (e3nn / PyG / torch_cluster are not installable here)')
         print(json.dumps({'metric': 'denoised samples/sec (20-step)', 'value': v, 'unit': 'samples/s', 'n_gpus': args.gpus,
                           'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000 * (time.time() - t0) / args.steps,
                           'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
@@ -169,7 +201,7 @@ def main():
     from diffphore_b200.sampler import DenoisingSampler
     from diffphore_b200.synthetic import make_pairs
     from diffphore_b200 import profiling
-    from tests.parity_util import random_state_dict
+    from diffphore_b200.synthetic import random_state_dict, real_example_pairs
     import __graft_entry__ as ge
     ge.build()
     torch.cuda.set_device(local)
@@ -178,11 +210,12 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     sd = random_state_dict(0)
     graphs = make_pairs(args.pairs, args.atoms, args.phore, first=rank * args.pairs)
+    ckpt = os.path.join(ROOT, 'oracle', '_ref', 'weights', 'best_ema_inference_epoch_model.pt')
+    shipped_sd = torch.load(ckpt, map_location='cpu', weights_only=False) if os.path.exists(ckpt) else None
     if args.real:
-        from tests.parity_util import load_pairs, have_checkpoint, real_state_dict
-        graphs = load_pairs('real', args.real)
+        graphs = real_example_pairs(args.real)
         args.pairs = len(graphs)
-        sd = real_state_dict() if have_checkpoint() else sd
+        sd = shipped_sd if shipped_sd is not None else sd
     w = ModelWeights(sd, dev)
     sampler = DenoisingSampler(w, INF_STEPS)
     n_samples_local = args.pairs * args.samples
@@ -269,12 +302,54 @@ def main():
         e2e = {'value': n_samples_local * world / float(te.item()), 'unit': 'samples/s',
                'h2d_bytes_per_step': int(sampler.last_h2d_bytes), 'd2h_bytes_per_step': int(pos.numel() * 4)}
 
+    # ---- the other BASELINE.json configurations, NOT the headline: same sampler API, one warm-up + two timed runs each
+    def side_config(graphs_x, sd_x, samples_x, what):
+        sm = sampler if sd_x is sd else DenoisingSampler(ModelWeights(sd_x, dev), INF_STEPS)
+        res_x = sm.prepare(graphs_x, samples_x)
+        n_x = len(graphs_x) * samples_x
+        tt = []
+        for k in range(3):
+            sm.reset(res_x, generator=gen)
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            sm.run_resident(res_x, generator=gen)
+            gather_poses(torch.cat([r[0].pos for r in res_x]))
+            a1.record()
+            barrier()
+            if k:
+                tt.append(a0.elapsed_time(a1))
+        del res_x
+        te_x = []
+        for k in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            pos_x, _ = sm.run(graphs_x, samples_x, generator=gen, pinned=True)
+            gather_poses(pos_x.to(dev, non_blocking=True)) if world > 1 else None
+            barrier()
+            if k:
+                te_x.append(time.perf_counter() - t0)
+        tm = torch.tensor([float(np.mean(tt)), 1e3 * float(np.mean(te_x))], device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        return {'workload': what, 'value': n_x * world / (float(tm[0]) / 1e3), 'e2e': n_x * world / (float(tm[1]) / 1e3),
+                'unit': 'samples/s', 'ms_per_job': float(tm[0]), 'e2e_ms_per_job': float(tm[1]), 'samples_per_gpu': n_x}
+
+    extra = None
+    if not args.no_extra and not args.real and (args.pairs, args.samples, args.atoms, args.phore) == (N_PAIRS, SAMPLES, N_ATOMS, N_PHORE):
+        extra = {}
+        g3 = real_example_pairs(15)
+        extra['cfg3_shape'] = side_config(g3, shipped_sd if shipped_sd is not None else sd, SAMPLES,
+                                          f'{len(g3)} real-shaped pairs (reference example ligands x the 79-node example pharmacophore) x {SAMPLES} samples, '
+                                          + ('shipped checkpoint' if shipped_sd is not None else 'random-init weights') + ', every rank runs the same job')
+        extra['cfg4'] = side_config(make_pairs(512, 64, 12, first=rank * 512), sd, SAMPLES,
+                                    f'synthetic 512 pairs per GPU (64 atoms / 12 phore points) x {SAMPLES} samples: 4096 pairs over 8 GPUs')
+        extra['cfg5'] = side_config(make_pairs(1, 128, 16), sd, SAMPLES,
+                                    f'1 pair (128 atoms / 16 phore points) x {SAMPLES} samples: latency-bound; every rank runs the same job')
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r, dt = cpu_reference_rate(8, 8, cores)
-        cpu = {'value': r, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
-               'sample': f'8 pairs x 8 samples x {INF_STEPS} steps of the cfg2 shape ({dt:.1f} s of CPU work, oracle port, '
-                         f'torch.set_num_threads({cores}))'}
+        cpu = cpu_baseline_block(cores)
     if rank == 0:
         print(json.dumps({'metric': 'denoised samples/sec (20-step)', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
                           'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
@@ -289,7 +364,7 @@ def main():
                                      'denoising_steps': INF_STEPS, 'l2': 'inputs larger than L2 (per conv: >= 130 MB of node features + 0.1-0.7 GB of per-edge hidden activations)',
                                      'parallelism': f'pairs sharded over {world} rank(s), one all_gather of poses'},
                           'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof,
-                          'kernels': prof.summary(), 'cpu_baseline': cpu}))
+                          'kernels': prof.summary(), 'cpu_baseline': cpu, 'other_configs_not_headline': extra}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -242,6 +242,10 @@ class ModelWeights:
         ns, nv = self.cfg['ns'], self.cfg['nv']
         if (ns, nv, self.cfg['num_conv_layers']) != (20, 10, 4):
             raise NotImplementedError('kernels are specialised for ns=20, nv=10, num_conv_layers=4 (shipped config)')
+        hard = dict(sigma_embed_dim=20, distance_embed_dim=20, cross_distance_embed_dim=20, max_neighbors=32)
+        bad = {k: self.cfg[k] for k, v in hard.items() if self.cfg[k] != v}
+        if bad or len(self.cfg['clash_cutoff']) != 5:
+            raise NotImplementedError(f'kernels hard-code {hard} and five clash cut-offs (shipped config); got {bad or self.cfg["clash_cutoff"]}')
         seq = [parse_irreps(s) for s in IRREP_SEQ(ns, nv)]
         sh = sh_irreps(2)
         sh45, _ = full_tp_irreps_out(sh, [(1, 2, 1)])

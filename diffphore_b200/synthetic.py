@@ -181,3 +181,44 @@ def make_pair(pair_id, n_atoms=32, n_phore=8, seed_base=1000):
 
 def make_pairs(n_pairs, n_atoms=32, n_phore=8, first=0):
     return [make_pair(first + i, n_atoms, n_phore) for i in range(n_pairs)]
+
+
+SHIPPED_MODEL_KW = dict(sigma_embed_dim=20, ns=20, nv=10, num_conv_layers=4, distance_embed_dim=20, cross_distance_embed_dim=20,
+                        consider_norm=True, boarder=True, use_phore_match_feat=True, cross_distance_transition=True,
+                        phore_direction_transition=True, phoretype_match_transition=True, atom_weight='phore',
+                        auto_phorefp=False, scaler=100.0, dropout=0.1, clash_cutoff=[1.0, 2.0, 3.0, 4.0, 5.0])
+
+
+def random_state_dict(seed=0):
+    """Random-init weights of the shipped architecture (model_parameters.yml; nn defaults) with non-trivial BatchNorm statistics:
+    what the synthetic benchmark configurations run (there is no dataset the shipped checkpoint is in distribution for).
+    Needs the reference-facing mirror `src/models/score_model_phore.py` on sys.path (bench.py / tests put it there)."""
+    import os
+    import sys
+    src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'src')
+    if src not in sys.path:
+        sys.path.insert(0, src)
+    from models.score_model_phore import TensorProductScoreModel
+    torch.manual_seed(seed)
+    m = TensorProductScoreModel(None, torch.device('cpu'), None, **SHIPPED_MODEL_KW)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(seed + 1)
+    for k in sd:
+        if k.endswith('batch_norm.running_var'):
+            sd[k] = torch.rand(sd[k].shape, generator=g) * 1.5 + 0.5
+        elif k.endswith('batch_norm.running_mean') or k.endswith('batch_norm.bias'):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.3
+        elif k.endswith('batch_norm.weight'):
+            sd[k] = torch.rand(sd[k].shape, generator=g) * 0.1 + 0.05     # small updates keep the random net well-conditioned
+    return sd
+
+
+def real_example_pairs(n_pairs, path=None):
+    """The reference's example ligands x its 79-node example pharmacophore as packed tensors (tests/golden/real_pairs.npz, made by
+    tools/make_real_inputs.py: pharmacophore side from the reference's own parser, ligand side from the reduced featuriser)."""
+    import os
+    from .graph import graph_from_arrays
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    a = np.load(path or os.path.join(root, 'tests', 'golden', 'real_pairs.npz'))
+    names = list(a['names'])
+    return [graph_from_arrays(a, f'p{k}_', str(names[k])) for k in range(min(n_pairs, len(names)))]

@@ -29,7 +29,14 @@ def read_sdf_block(text):
         xyz.append([float(l[0:10]), float(l[10:20]), float(l[20:30])])
         elem.append(l[31:34].strip())
     bonds = [(int(l[0:3]) - 1, int(l[3:6]) - 1, int(l[6:9])) for l in L[4 + na:4 + na + nb]]
-    return L[0].strip(), elem, np.asarray(xyz, dtype=np.float64), bonds, L[:4 + na + nb]
+    # keep the property block (M  CHG / M  ISO / M  RAD ...) up to M  END: most non-RDKit writers carry charges only there
+    props = []
+    for l in L[4 + na + nb:]:
+        if l.startswith('M  END') or l.startswith('$$$$'):
+            break
+        if l.startswith('M  '):
+            props.append(l)
+    return L[0].strip(), elem, np.asarray(xyz, dtype=np.float64), bonds, L[:4 + na + nb] + props
 
 
 def transformation_mask(n, bonds):
@@ -147,6 +154,24 @@ def ligand_graph_from_sdf(path, graph, rng=None):
     return graph
 
 
+def _reindexed_property_lines(props, keep):
+    """`M  CHG` / `M  ISO` / `M  RAD` lines of the input mol block (count + (atom, value) pairs in 4-column fields) re-indexed to
+    the heavy-atom numbering; entries on removed hydrogens are dropped, other `M  ` lines are passed through unchanged."""
+    out = []
+    for l in props:
+        tag = l[3:6]
+        if tag in ('CHG', 'ISO', 'RAD'):
+            f = l[6:].split()
+            pairs = [(int(f[1 + 2 * k]) - 1, f[2 + 2 * k]) for k in range(int(f[0]))]
+            pairs = [(keep[a] + 1, v) for a, v in pairs if a in keep]
+            for k in range(0, len(pairs), 8):
+                part = pairs[k:k + 8]
+                out.append(f'M  {tag}{len(part):3d}' + ''.join(f'{a:4d}{int(v):4d}' for a, v in part))
+        elif not l.startswith('M  END'):
+            out.append(l)
+    return out
+
+
 def write_mol_with_multi_coords(template, multi_new_coords, path, name, marker='', properties=None):
     """SD file with one record per pose: the heavy-atom coordinates of the input mol block are substituted
     (process_mols.py:888-921 does the same through RDKit on the H-stripped molecule; hydrogens keep their input
@@ -159,6 +184,7 @@ def write_mol_with_multi_coords(template, multi_new_coords, path, name, marker='
         a, b = int(l[0:3]) - 1, int(l[3:6]) - 1
         if a in keep and b in keep:
             bond_lines.append(f'{keep[a] + 1:3d}{keep[b] + 1:3d}' + l[6:])
+    prop_lines = _reindexed_property_lines(lines[4 + na + nb:], keep)
     with open(path, 'w') as fh:
         for i, coords in enumerate(multi_new_coords):
             fh.write(f'{name}_{marker}_{i}\n{lines[1]}\n{lines[2]}\n')
@@ -167,6 +193,8 @@ def write_mol_with_multi_coords(template, multi_new_coords, path, name, marker='
                 x, y, z = (float(v) for v in coords[k])
                 fh.write(f'{x:10.4f}{y:10.4f}{z:10.4f}' + lines[4 + a][30:] + '\n')
             for l in bond_lines:
+                fh.write(l + '\n')
+            for l in prop_lines:
                 fh.write(l + '\n')
             fh.write('M  END\n')
             if properties:

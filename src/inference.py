@@ -6,8 +6,11 @@
 
 Differences by design: `fit` batches ACROSS pairs: pending pairs x samples are denoised in jobs of
 ~4096 graphs by one DenoisingSampler instead of one pair at a time, and the SD writing + AncPhore scoring of a finished
-job overlaps the next job (PoseSink); per-pair `run_time` is the job time divided evenly over its pairs.  Preprocessing: RDKit path when RDKit is importable (not in this image), else the
-reduced RDKit-free featuriser for 3-D SD files (datasets/process_mols.py).  Scoring: AncPhore binary when available
+job overlaps the next job (PoseSink); per-pair `run_time` is the job time divided evenly over its pairs.  Preprocessing: ALWAYS the
+reduced RDKit-free featuriser for 3-D SD files (datasets/process_mols.py: crude aromaticity / hybridisation / charge / chirality
+and phorefp / norm typing; RDKit is absent from this image and no RDKit branch exists) - a warning is printed once per run;
+poses and fitscores of real ligands are therefore NOT comparable one-to-one with the reference's RDKit pipeline
+(process_mols.py:255-417).  SMILES / .smi ligands pass read_input but are skipped (no conformer generation without RDKit).  Scoring: AncPhore binary when available
 (`--ancphore_path`), else fitscore = -2.0 like the reference's failure sentinel (inference.py:235-237).
 """
 import _bootstrap  # noqa: F401  (repo root on sys.path)
@@ -103,6 +106,11 @@ def build_graph(record):
     """generate_graph (datasets/pdbbind_phore.py:1143-1188) for one record: ligand + pharmacophore tensors, phoretype
     one-hot, everything centred on the pharmacophore centroid (kept in `original_center`)."""
     lig_file, phore_file = record['ligand_description'], record['phore']
+    if not build_graph.warned:
+        build_graph.warned = True
+        warnings.warn('RDKit-free REDUCED ligand featuriser active (no RDKit in this image): atom features, phorefp and norm typing '
+                      'are approximations of process_mols.py:193-417; poses / fitscores are not comparable one-to-one with the '
+                      "reference's RDKit pipeline", stacklevel=2)
     if not (os.path.exists(lig_file) and lig_file.endswith('.sdf')):
         raise NotImplementedError('without RDKit only 3-D .sdf ligands can be ingested (SMILES needs conformer generation)')
     g = HeteroGraph()
@@ -118,6 +126,9 @@ def build_graph(record):
     g.name = f"{phore.id}__{os.path.splitext(os.path.basename(lig_file))[0]}"
     g.phore_file = phore_file
     return g
+
+
+build_graph.warned = False
 
 
 def get_perfect_similarity(g, weights=(1.0, 1.0, 1.0, 1.0, 1.0, 0.0, 1.0, 1.0, 1.0, 1.0, 0.0),      # HY and EX do not count
@@ -207,7 +218,9 @@ def fit(args, model, complex_graphs, device, t_to_sigma, tmp_log='', n_report=10
                                no_final_step_noise=args.no_final_step_noise, ode=getattr(args, 'ode', False))
     gen = None
     if getattr(args, 'seed', None) is not None:
-        gen = torch.Generator(device=device).manual_seed(args.seed)
+        # one stream per rank: under torchrun every rank denoises different pairs (round-robin), so equal seeds would hand them
+        # identical initial-pose / noise streams
+        gen = torch.Generator(device=device).manual_seed(args.seed + int(os.environ.get('RANK', 0)))
     keep = bool(getattr(args, 'keep_update', False))
     done, todo = {}, []
     for g in complex_graphs:
@@ -226,6 +239,13 @@ def fit(args, model, complex_graphs, device, t_to_sigma, tmp_log='', n_report=10
             print(f'[W] Graph {g.name} with 0 atoms, skipped')
         else:
             todo.append(g)
+    seen = {}
+    for g in todo:                                      # duplicate names would make two sink tasks write the same files
+        k = seen.get(g.name, 0)
+        seen[g.name] = k + 1
+        if k:
+            print(f'[W] duplicate pair name `{g.name}`: outputs of this copy go to `{g.name}_dup{k}`')
+            g.name = f'{g.name}_dup{k}'
     sink = PoseSink(args, workers=min(getattr(args, 'num_workers', 8) or 1, os.cpu_count() or 1))
     initial_poses, dock_poses = {}, {}
     n_done, std_time = 0, time.time()
@@ -234,14 +254,17 @@ def fit(args, model, complex_graphs, device, t_to_sigma, tmp_log='', n_report=10
         t0 = time.time()
         pos, ptr = sampler.run(job, N, no_random=args.no_random, generator=gen, no_torsion=args.no_torsion, keep_update=keep)
         run_time = (time.time() - t0) / len(job)
+        out = []
         for i, g in enumerate(job):
             n, lo = g['ligand'].pos.shape[0], ptr[i * N]
             center = g.original_center.numpy()
-            sink.submit(g, pos[lo:lo + N * n].reshape(N, n, 3).numpy() + center, run_time)
+            out.append((g, pos[lo:lo + N * n].reshape(N, n, 3).numpy() + center))
             if keep:                                    # inference.py:191-192,247-248 (initial pose, pose after every step)
                 traj = sampler.last_trajectory[:, lo:lo + N * n].reshape(-1, N, n, 3).numpy()
                 initial_poses[g.name] = [traj[0, s] for s in range(N)]
                 dock_poses[g.name] = [[traj[k, s] for k in range(1, traj.shape[0])] for s in range(N)]
+        for g, poses in out:                            # hand-off only once the WHOLE job succeeded: the pair-by-pair fallback
+            sink.submit(g, poses, run_time)             # below must never find a pair of this job already submitted
 
     pairs_cap = sampler.graphs_per_chunk(todo, N) if todo else 1
     jobs = plan_jobs(todo, N, getattr(args, 'pairs_per_job', None) or pairs_cap)

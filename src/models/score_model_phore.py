@@ -167,7 +167,8 @@ class TensorProductScoreModel(nn.Module):
         self.ns, self.nv, self.no_torsion, self.scaler = ns, nv, no_torsion, scaler
         self.lig_max_radius, self.cross_max_distance, self.center_max_distance = lig_max_radius, cross_max_distance, center_max_distance
         self.clash_cutoff = list(clash_cutoff)
-        self.sigma_embed_dim = sigma_embed_dim
+        self.sigma_embed_dim, self.num_conv_layers = sigma_embed_dim, num_conv_layers
+        self.distance_embed_dim, self.cross_distance_embed_dim = distance_embed_dim, cross_distance_embed_dim
         self.encoder = LigPhoreEncoder(device, timestep_emb_func, in_lig_edge_features, sigma_embed_dim, sh_lmax, ns, nv,
                                        num_conv_layers, distance_embed_dim, cross_distance_embed_dim, lig_max_radius,
                                        phore_max_radius, cross_max_distance, dropout, num_phoretype, clash_cutoff, batch_norm)
@@ -196,10 +197,32 @@ class TensorProductScoreModel(nn.Module):
         return out
 
     def kernel_weights(self, device=None):
+        """ModelWeights for the kernels.  EVERY schedule / embedding parameter the kernels or the per-step constant block use is
+        taken from this model's constructor arguments and callables - never silently from engine.DEFAULT_CONFIG: the noise
+        schedule is read off `self.t_to_sigma` (sigma_min = t_to_sigma(0), sigma_max = t_to_sigma(1), diffusion_utils.py:16-20),
+        and `self.timestep_emb_func` must be the sinusoidal embedding the constant block folds (diffusion_utils.py:82-132)."""
         device = torch.device(device or self.device)
         if self._kernel_weights is None or self._kernel_weights.device != device:
             cfg = dict(lig_max_radius=self.lig_max_radius, cross_max_distance=self.cross_max_distance,
-                       center_max_distance=self.center_max_distance, scaler=self.scaler, clash_cutoff=self.clash_cutoff)
+                       center_max_distance=self.center_max_distance, scaler=self.scaler, clash_cutoff=self.clash_cutoff,
+                       ns=self.ns, nv=self.nv, num_conv_layers=self.num_conv_layers, sigma_embed_dim=self.sigma_embed_dim,
+                       distance_embed_dim=self.distance_embed_dim, cross_distance_embed_dim=self.cross_distance_embed_dim)
+            if self.t_to_sigma is not None:
+                lo, hi = self.t_to_sigma(0.0, 0.0, 0.0), self.t_to_sigma(1.0, 1.0, 1.0)
+                for k, a, b in zip(('tr', 'rot', 'tor'), lo, hi):
+                    cfg[f'{k}_sigma_min'], cfg[f'{k}_sigma_max'] = float(a), float(b)
+                mid = self.t_to_sigma(0.5, 0.5, 0.5)                   # the kernels assume the geometric schedule
+                for k, m in zip(('tr', 'rot', 'tor'), mid):
+                    if abs(float(m) - (cfg[f'{k}_sigma_min'] * cfg[f'{k}_sigma_max']) ** 0.5) > 1e-6 * float(m):
+                        raise NotImplementedError('t_to_sigma is not sigma_min^(1-t) sigma_max^t (diffusion_utils.py:16-20)')
+            if self.timestep_emb_func is not None:
+                from diffphore_b200.engine import DEFAULT_CONFIG, sinusoidal_embedding
+                probe = torch.tensor([0.37])
+                got = self.timestep_emb_func(probe)[0].float().cpu()
+                want = sinusoidal_embedding(0.37, self.sigma_embed_dim, DEFAULT_CONFIG['embedding_scale'])
+                if got.shape != want.shape or not torch.allclose(got, want, atol=1e-5):
+                    raise NotImplementedError('only the sinusoidal timestep embedding with embedding_scale=10000 is implemented '
+                                              'on the B200 path (model_parameters.yml: embedding_type / embedding_scale)')
             self._kernel_weights = ModelWeights({k: v.detach().cpu() for k, v in self.state_dict().items()}, device, cfg)   # folding runs on the host
         return self._kernel_weights
 

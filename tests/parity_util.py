@@ -30,21 +30,7 @@ def real_state_dict():
     return torch.load(LOCAL_CKPT, map_location='cpu', weights_only=False)
 
 
-def random_state_dict(seed=0):
-    """Random-init weights of the shipped architecture (nn defaults), with non-trivial BatchNorm statistics."""
-    from models.score_model_phore import TensorProductScoreModel
-    torch.manual_seed(seed)
-    m = TensorProductScoreModel(None, torch.device('cpu'), None, **SHIPPED_KW)
-    sd = {k: v.clone() for k, v in m.state_dict().items()}
-    g = torch.Generator().manual_seed(seed + 1)
-    for k in sd:
-        if k.endswith('batch_norm.running_var'):
-            sd[k] = torch.rand(sd[k].shape, generator=g) * 1.5 + 0.5
-        elif k.endswith('batch_norm.running_mean') or k.endswith('batch_norm.bias'):
-            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.3
-        elif k.endswith('batch_norm.weight'):
-            sd[k] = torch.rand(sd[k].shape, generator=g) * 0.1 + 0.05     # small updates keep the random net well-conditioned
-    return sd
+from diffphore_b200.synthetic import random_state_dict  # noqa: E402,F401  (lives in the package: bench.py uses it too)
 
 
 def load_pairs(kind, n_pairs, n_atoms=32, n_phore=8):
