@@ -39,7 +39,7 @@ __device__ __forceinline__ void dp_sh9(float vx, float vy, float vz, float* sh) 
 #define DP_RBF_PHORE 1
 #define DP_RBF_CROSS 2
 #define DP_RBF_CENTER 3
-__constant__ DpConstants c_dp;   // single translation unit (dp_abi.cu)
+static __constant__ DpConstants c_dp;   // used by dp_abi.cu only (static: conv_fused2.cu includes this header too)
 
 __device__ __forceinline__ void dp_rbf20(float d, int which, float* out) {
     const float coeff = c_dp.rbf_coeff[which];

@@ -66,7 +66,16 @@ class ConvWeights:
                 # weight-column layout of dp_conv_fused: 'flat_trim' (default: consecutive 112-column chunks, last MMA trimmed;
                 # measured +3.3 % on the cfg2 step, profiles/ab_flat_r2.txt), 'flat', or 'paths' (100-column path-aligned chunks)
                 layout = os.environ.get('DIFFPHORE_W2', 'flat_trim')
-                if layout in ('flat', 'flat_trim'):
+                # generation of the fused kernel: 'auto' (default) = dp_conv_fused2 (csrc/conv_fused2.cuh: next pair tile's operands
+                # prepared by a dedicated warpgroup) where it measured faster on the B200 - the short weight streams of layer 0 and the
+                # torsion convolution - and dp_conv_fused elsewhere; '1' / '2' force one generation (results are identical bit for bit)
+                gen = os.environ.get('DIFFPHORE_CONV_GEN', 'auto')
+                self.gen = (2 if layer_id in (L.TP_L0, L.TP_TOR) else 1) if gen == 'auto' else int(gen)
+                if self.gen == 2:
+                    img, s96 = _make_w2imgflat(_f32(w3).cpu(), _f32(sd[prefix + '.fc.3.bias']).cpu(), 96)
+                    assert s96 == self.inv_wscale
+                    self.w2img96 = img.to(device)
+                elif layout in ('flat', 'flat_trim'):
                     img, sflat = _make_w2imgflat(_f32(w3).cpu(), _f32(sd[prefix + '.fc.3.bias']).cpu())
                     assert sflat == self.inv_wscale
                     self.w2imgflat = img.to(device)
@@ -137,22 +146,23 @@ def _make_w2img112(w3, b3):
     return img.contiguous().reshape(-1).view(torch.uint8), 2.0 ** (-k)
 
 
-def _make_w2imgflat(w3, b3):
-    """EXPERIMENTAL layout for dp_conv_fused_flat: like _make_w2img112, but the W columns are cut into consecutive 112-column
-    chunks regardless of the path boundaries (zero padding in the last chunk only): [ceil(W/112)][hi|lo][k/8][14][8][8] fp16.
-    Same power-of-two scale as _make_w2img112 (the maximum is the same).  Returns (uint8 image tensor, 2^-k)."""
+def _make_w2imgflat(w3, b3, n=112):
+    """Flat layout for dp_conv_fused_flat (n = 112) and dp_conv_fused2 (n = 96): like _make_w2img112, but the W columns are cut into
+    consecutive n-column chunks regardless of the path boundaries (zero padding in the last chunk only):
+    [ceil(W/n)][hi|lo][k/8][n/8][8][8] fp16.  Same power-of-two scale as _make_w2img112 (the maximum is the same).
+    Returns (uint8 image tensor, 2^-k)."""
     W = w3.shape[0]
-    nch = (W + 111) // 112
-    x = torch.zeros(nch * 112, 64, dtype=torch.float32)
+    nch = (W + n - 1) // n
+    x = torch.zeros(nch * n, 64, dtype=torch.float32)
     x[:W, :60] = w3
     x[:W, 60] = b3
-    x = x.reshape(nch, 112, 64)
+    x = x.reshape(nch, n, 64)
     m = float(x.abs().max())
     k = 12 - math.floor(math.log2(m)) if m > 0 and math.isfinite(m) else 0
     xs = x * (2.0 ** k)
     hi = xs.half()
     lo = (xs - hi.float()).half()
-    img = torch.stack([hi, lo], 1).reshape(nch, 2, 14, 8, 8, 8).permute(0, 1, 4, 2, 3, 5)     # [c][h][kc][ng][r][j]
+    img = torch.stack([hi, lo], 1).reshape(nch, 2, n // 8, 8, 8, 8).permute(0, 1, 4, 2, 3, 5)     # [c][h][kc][ng][r][j]
     return img.contiguous().reshape(-1).view(torch.uint8), 2.0 ** (-k)
 
 
@@ -618,8 +628,11 @@ class Engine:
             e0 = tm.start()
         if self.use_fused and tiles is not None and cw.w2img112 is not None:
             tile_node, n_tiles_dev, n_tiles_cap = tiles
-            flat = getattr(cw, 'w2imgflat', None)                      # EXPERIMENTAL weight layout (DIFFPHORE_W2=flat)
+            flat = getattr(cw, 'w2imgflat', None)                      # weight layout of the first-generation kernel (DIFFPHORE_W2)
             fn = self.lib.dp_conv_fused if flat is None else self.lib.dp_conv_fused_flat
+            if getattr(cw, 'gen', 1) == 2:
+                flat, fn = cw.w2img96, self.lib.dp_conv_fused2
+                cw.flat_mode_bits = 0
             L.check(fn(cw.layer_id, p(emb), p(perm), p(tb), p(idxB), tb.shape[1], p(tc), p(idxC), p(idxC2),
                                            tc.shape[1], p(cw.w1img), cw.inv_w1scale, p(cw.w2img112 if flat is None else flat), cw.inv_wscale, p(node_in),
                                            p(gather), p(sh), sh_stride, p(seg), p(tile_node), p(n_tiles_dev), n_tiles_cap,

@@ -49,6 +49,7 @@ _SIGNATURES = {
     'dp_build_tiles': ([P, P, i32, P, P, P, P, P], i32),
     'dp_conv_fused': ([i32, P, P, P, P, i32, P, P, P, i32, P, C.c_float, P, C.c_float, P, P, P, i32, P, P, P, i32, P, P, P, P, i32, i32, P], i32),
     'dp_conv_fused_flat': ([i32, P, P, P, P, i32, P, P, P, i32, P, C.c_float, P, C.c_float, P, P, P, i32, P, P, P, i32, P, P, P, P, i32, i32, P], i32),
+    'dp_conv_fused2': ([i32, P, P, P, P, i32, P, P, P, i32, P, C.c_float, P, C.c_float, P, P, P, i32, P, P, P, i32, P, P, P, P, i32, i32, P], i32),
     'dp_tp_scatter': ([i32, P, P, P, P, i32, P, P, P, P, P, P, i32, i32, i32, P], i32),
     'dp_center_step': ([P, P, i32, C.POINTER(DpSmallWeights), P, P, P, P], i32),
     'dp_score_head': ([P, i32, C.POINTER(DpSmallWeights), P, P, P, P], i32),

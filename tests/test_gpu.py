@@ -349,7 +349,7 @@ def _conv_case(layer, degs, seed=0, shift=0, n_in=700):
     return t
 
 
-def _run_conv_fused(layer, t, lib, mode=0, residual=None, out0=None, flat=False, trim=False):
+def _run_conv_fused(layer, t, lib, mode=0, residual=None, out0=None, flat=False, trim=False, gen2=False):
     from diffphore_b200.engine import _make_w1img, _make_w2img112, _make_w2imgflat, greedy_tiles
     L, p, dev = lib, lib.ptr, torch.device('cuda:0')
     d_in, d_out, W, shs = _CF[layer]
@@ -358,12 +358,14 @@ def _run_conv_fused(layer, t, lib, mode=0, residual=None, out0=None, flat=False,
     tile_node = torch.tensor(tiles + [len(t['degs'])], dtype=torch.int32, device=dev)
     img1, inv1 = _make_w1img(t['w1'], t['b1'])
     img2, inv2 = (_make_w2imgflat if flat else _make_w2img112)(t['w3'], t['b3'])
+    if gen2:
+        img2, inv2 = _make_w2imgflat(t['w3'], t['b3'], 96)
     d = {k: v.to(dev) for k, v in t.items() if torch.is_tensor(v)}
     img1, img2 = img1.to(dev), img2.to(dev)
     out = torch.zeros(len(t['degs']), d_out, device=dev) if out0 is None else out0.clone().to(dev)
     res = None if residual is None else residual.to(dev)
     st = torch.cuda.current_stream().cuda_stream
-    fn = L.load().dp_conv_fused_flat if flat else L.load().dp_conv_fused
+    fn = L.load().dp_conv_fused2 if gen2 else (L.load().dp_conv_fused_flat if flat else L.load().dp_conv_fused)
     L.check(fn(layer, p(d['emb']), None, p(d['tb']), p(d['ib']), 100, p(d['tb']), p(d['ic']), None, 100, p(img1),
                                    inv1, p(img2), inv2, p(d['nodes']), p(d['gat']), p(d['sh']), shs, p(seg), p(tile_node), None,
                                    len(tiles), p(d['oscale']), p(d['oshift']), p(out), p(res), 0 if res is None else res.shape[1],
@@ -395,6 +397,31 @@ def _conv_reference(layer, t):
     node = torch.from_numpy(np.repeat(np.arange(len(t['degs'])), t['degs']))
     out = torch.zeros(len(t['degs']), y.shape[1], dtype=torch.float64).index_add_(0, node, y)
     return out / torch.from_numpy(np.maximum(t['degs'], 1)).double()[:, None]
+
+
+@pytest.mark.parametrize('layer', [0, 1, 2, 3, 5])
+@pytest.mark.parametrize('window', ['narrow', 'wide'])
+def test_conv_fused2_is_bit_identical_to_the_first_generation(built_lib, layer, window):
+    """dp_conv_fused2 (operands of the next pair tile prepared by a dedicated warpgroup, 96-column flat chunks, node-row window in
+    shared memory, output staged in parts) computes the same products in the same order as dp_conv_fused: outputs must be equal
+    bit for bit, for gather windows that fit shared memory ('narrow': sources within 60 consecutive rows, like the atoms of one or two
+    graphs) and for windows that do not ('wide': rows read from global memory), all three output modes, many pair tiles per CTA."""
+    rng = np.random.default_rng(100 + layer)
+    degs = np.concatenate([rng.integers(0, 40, 150), [128, 0, 1, 127, 3, 256, 100, 79, 79, 79, 200, 5], rng.integers(1, 30, 6000)])
+    t = _conv_case(layer, degs, seed=layer)
+    if window == 'narrow':
+        E = t['gat'].shape[0]
+        base = (torch.arange(E) // 256 * 7) % 600                      # a window that moves from pair tile to pair tile
+        t['gat'] = (base + torch.randint(0, 60, (E,), generator=torch.Generator().manual_seed(layer))).to(torch.int32)
+    d_in, d_out = _CF[layer][0], _CF[layer][1]
+    g = torch.Generator().manual_seed(7)
+    res, out0 = torch.randn(len(t['degs']), d_in, generator=g), torch.randn(len(t['degs']), d_out, generator=g)
+    for mode, kw in ((0, {}), (1, dict(residual=res)), (2, dict(out0=out0))):
+        if mode == 1 and layer == 5:
+            continue
+        ref = _run_conv_fused(layer, t, built_lib, mode=mode, **kw)
+        got = _run_conv_fused(layer, t, built_lib, mode=mode, gen2=True, **kw)
+        assert torch.equal(got, ref), (layer, window, mode, float((got - ref).abs().max()))
 
 
 @pytest.mark.parametrize('layer', [0, 1, 2, 3, 5])

@@ -6,7 +6,9 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'src'))
 from diffphore_b200 import lib as L
 from diffphore_b200.engine import _make_w2img, _make_w2img112, _make_w2imgflat, _make_w1img, greedy_tiles
 
-FLAT = os.environ.get('DIFFPHORE_W2', 'paths') == 'flat'      # time the experimental flat weight layout (dp_conv_fused_flat)
+FLAT = os.environ.get('DIFFPHORE_W2', 'paths') == 'flat'      # time the flat weight layout (dp_conv_fused_flat)
+GEN2 = os.environ.get('DIFFPHORE_CONV_GEN', '1') == '2'       # time dp_conv_fused2 (96-column flat chunks)
+NARROW = os.environ.get('PROBE_WINDOW', 'narrow') == 'narrow'  # gather sources within 60 consecutive rows per pair tile (like one or two graphs)
 import numpy as np
 lib = L.load(); p = L.ptr
 dev = torch.device('cuda:0')
@@ -25,14 +27,20 @@ def run(layer, n_nodes, deg, seed=0, mode=0, reps=3):
     nodes20 = torch.randn(n_in, 100, generator=g).to(dev)
     ib = torch.randint(0, n_in, (E,), generator=g, dtype=torch.int32).to(dev)
     ic = torch.randint(0, n_in, (E,), generator=g, dtype=torch.int32).to(dev)
-    gat = torch.randint(0, n_in, (E,), generator=g, dtype=torch.int32).to(dev)
+    gat = torch.randint(0, n_in, (E,), generator=g, dtype=torch.int32)
+    if NARROW:
+        gat = ((torch.arange(E) // 256 * 7) % (n_in - 100) + torch.randint(0, 60, (E,), generator=g)).to(torch.int32)
+    gat = gat.to(dev)
     sh = torch.randn(E, shs, generator=g).to(dev)
     w1c, b1c = torch.randn(60, 60, generator=g) / 8, torch.randn(60, generator=g)
     w1, b1 = w1c.to(dev), b1c.to(dev)
     img1, inv1 = _make_w1img(w1c, b1c); img1 = img1.to(dev)
     w3, b3 = torch.randn(W, 60, generator=g) / 8, torch.randn(W, generator=g)
     img, inv_ws = _make_w2img(w3, b3); img = img.to(dev)
-    img112, inv2 = (_make_w2imgflat if FLAT else _make_w2img112)(w3, b3); img112 = img112.to(dev)
+    img112, inv2 = (_make_w2imgflat if FLAT else _make_w2img112)(w3, b3)
+    if GEN2:
+        img112, inv2 = _make_w2imgflat(w3, b3, 96)
+    img112 = img112.to(dev)
     assert inv_ws == inv2
     oscale, oshift = torch.rand(d_out, generator=g).to(dev) + 0.5, torch.randn(d_out, generator=g).to(dev)
     segd = torch.from_numpy(seg).to(dev)
@@ -52,7 +60,7 @@ def run(layer, n_nodes, deg, seed=0, mode=0, reps=3):
                                   p(res), d_in, mode, n_nodes, st), 'tp')
 
     def fused(out):
-        L.check((lib.dp_conv_fused_flat if FLAT else lib.dp_conv_fused)(layer, p(emb), None, p(nodes20), p(ib), 100, p(nodes20), p(ic), None, 100, p(img1), inv1, p(img112),
+        L.check((lib.dp_conv_fused2 if GEN2 else (lib.dp_conv_fused_flat if FLAT else lib.dp_conv_fused))(layer, p(emb), None, p(nodes20), p(ib), 100, p(nodes20), p(ic), None, 100, p(img1), inv1, p(img112),
                                   inv_ws, p(nodes), p(gat), p(sh), shs, p(segd), p(tile_node), None, n_tiles, p(oscale), p(oshift),
                                   p(out), p(res), d_in, mode, st), 'fused')
 
