@@ -189,6 +189,9 @@ TILE_GROUP = 8      # consecutive graphs whose nodes share one run of tiles (the
 TILE_EDGES = 256    # edges (and nodes) per pair tile of dp_conv_fused: two M = 128 MMA operands
 
 
+HOST_PACK_MAX_GRAPHS = 64    # batches of up to this many (pair, sample) graphs are expanded on the host (PackedBatch)
+
+
 def grouped_tiles(deg, nodes_per_graph, group=TILE_GROUP, cap=TILE_EDGES):
     """greedy_tiles restarted at every group of `group` consecutive graphs instead of at every graph, for ALL groups at once
     (numpy, vectorised across groups; the walk over a group's nodes stays sequential like tile_walk in conv_fused.cuh).
@@ -412,11 +415,19 @@ class PackedBatch:
         pa = [_pair_arrays(g) for g in graphs]
         Np = len(pa)
         B = Np * S
-        self.B, self.S, self.device = B, S, device = B, S, torch.device(device)
+        self.B, self.S, self.device = B, S, torch.device(device)
         self.h2d_bytes = 0
+        # Small batches (the reference-facing forward(data) / 4-40 sample jobs) are expanded on the HOST and uploaded as finished
+        # arrays: the index arithmetic below is ~270 tiny ATen kernels on the device, which cost more than the whole score model
+        # there.  Large batches keep the device-side expansion (only per-pair arrays cross PCIe).  Same arithmetic either way.
+        final_device = self.device
+        device = torch.device('cpu') if (final_device.type == 'cuda' and B <= HOST_PACK_MAX_GRAPHS) else final_device
+        on_host = device != final_device
 
         def up(a):
             t = torch.from_numpy(np.ascontiguousarray(a))
+            if on_host:
+                return t
             self.h2d_bytes += t.numel() * t.element_size()
             if device.type == 'cuda':
                 return t.pin_memory().to(device, non_blocking=True)
@@ -533,16 +544,31 @@ class PackedBatch:
         self.ppos, self.pnorm, self.ptype = (f32c(kk)[phs.src].contiguous() for kk in ('ppos', 'pnorm', 'ptype'))
         # static parts of the AtomEncoders (setup-time gathers; smp:64-73), evaluated once per pair
         w = weights
+        lig_tables, ph_tables, ph_lin_w = w.lig_tables, w.ph_tables, w.ph_lin_w
+        if on_host:
+            lig_tables = [w.h[f'encoder.lig_node_embedding.atom_embedding_list.{i}.weight'] for i in range(16)]
+            ph_tables = [w.h[f'encoder.phore_node_embedding.atom_embedding_list.{i}.weight'] for i in range(3)]
+            ph_lin_w = w.h['encoder.phore_node_embedding.linear.weight']
         x, px = up(np.concatenate([q.x for q in pa], 0).astype(np.int64)), f32c('px')
         ls = torch.zeros(x.shape[0], 20, device=device)
         for i in range(16):
-            ls = ls + w.lig_tables[i][x[:, i]]
+            ls = ls + lig_tables[i][x[:, i]]
         ps = torch.zeros(px.shape[0], 20, device=device)
         for i in range(3):
-            ps = ps + w.ph_tables[i][px[:, i].long()]
+            ps = ps + ph_tables[i][px[:, i].long()]
         # explicit products in a fixed order (a cuBLAS matmul may pick a size-dependent kernel => batch-composition-dependent rounding)
-        ps = ps + px[:, 3:4] * w.ph_lin_w[:, 0][None, :] + px[:, 4:5] * w.ph_lin_w[:, 1][None, :]
+        ps = ps + px[:, 3:4] * ph_lin_w[:, 0][None, :] + px[:, 4:5] * ph_lin_w[:, 1][None, :]
         self.lig_static, self.ph_static = ls[atoms.src].contiguous(), ps[phs.src].contiguous()
+        if on_host:                                     # finished arrays -> device (plain copies, no kernels)
+            def mv(v):
+                if torch.is_tensor(v):
+                    self.h2d_bytes += v.numel() * v.element_size()
+                    return v.contiguous().to(final_device)
+                if isinstance(v, tuple):
+                    return tuple(mv(t) for t in v)
+                return v
+            for k in list(self.__dict__):
+                self.__dict__[k] = mv(self.__dict__[k])
 
 
 class Workspace:

@@ -39,7 +39,7 @@ class DenoisingSampler:
         self.torus = torus_norm or TorusScoreNorm()
         self.weight_buffer_bytes = weight_buffer_bytes
         self.resident_bytes = resident_bytes
-        # small chunks are launch-bound: replay one captured step graph per denoising step (see _step_graph)
+        # small chunks are launch-bound: the whole loop of a chunk is replayed as one captured CUDA graph (see _loop_graph)
         self.cuda_graphs, self.graph_max_graphs = cuda_graphs, graph_max_graphs
         self.no_final_step_noise = no_final_step_noise
         self.ode = ode                                   # --ode: 0.5 g^2 dt score, no noise (sampling.py:226-228)
@@ -110,35 +110,49 @@ class DenoisingSampler:
             g_off += b.B
             r_off += b.n_rot
 
-    def _step_graph(self, b, ws, no_torsion, with_noise):
-        """One denoising step (score model + conformer update, 43 launches) captured as a CUDA graph.  Every kernel argument
-        is a pointer into the chunk's static buffers; per-step inputs go through `sc_buf` / `z_buf`, dynamic edge and tile
-        counts are read on the device, so one graph serves all steps of the chunk.  Launch-bound small jobs (cfg1 / cfg5
-        shapes: 4-40 graphs) spend ~0.5 ms per step in Python + launch overhead otherwise."""
-        key = (bool(no_torsion), bool(with_noise))
+    def _noise_buffers(self, b, ws):
+        """Static per-chunk noise buffers for ALL steps ([steps, B, 3], [steps, B, 3], [steps, n_rot]): filled once per job before the
+        loop (sampling.py:230-244 draws them step by step on the host), so that the loop itself launches nothing but our kernels."""
+        if not hasattr(ws, 'z_all'):
+            dev = self.w.device
+            ws.z_all = (torch.zeros(self.steps, b.B, 3, device=dev), torch.zeros(self.steps, b.B, 3, device=dev),
+                        torch.zeros(self.steps, max(b.n_rot, 1), device=dev))
+        return ws.z_all
+
+    def _step_args(self, ws, k, noise_mode):
+        """(constants, tr_z, rot_z, tor_z) of step k: views into static tensors (CUDA-graph capturable)."""
+        last = k == self.steps - 1
+        if noise_mode == 'none' or (noise_mode == 'all_but_last' and last):
+            return self.consts[k], None, None, None
+        return self.consts[k], ws.z_all[0][k], ws.z_all[1][k], ws.z_all[2][k]
+
+    def _loop_graph(self, b, ws, no_torsion, noise_mode):
+        """The WHOLE denoising loop of a chunk (steps x (score model + conformer update), 43 launches each) captured as ONE CUDA
+        graph.  Every kernel argument is a pointer into the chunk's static buffers: step k reads its constants from consts[k] and
+        its noise from z_all[:, k]; dynamic edge and tile counts are read on the device.  Launch-bound small jobs (cfg1 / cfg5
+        shapes: 4-40 graphs) spend ~0.5 ms per step in Python + launch overhead otherwise; between two replays nothing else runs."""
+        key = (bool(no_torsion), noise_mode)
         cache = ws.__dict__.setdefault('_graphs', {})
         if key in cache:
             return cache[key]
-        dev = self.w.device
-        if not hasattr(ws, 'sc_buf'):
-            ws.sc_buf = torch.zeros_like(self.consts[0])
-            ws.z_buf = (torch.zeros(b.B, 3, device=dev), torch.zeros(b.B, 3, device=dev), torch.zeros(max(b.n_rot, 1), device=dev))
-        z = ws.z_buf if with_noise else (None, None, None)
+        self._noise_buffers(b, ws)
         n_before = ws.n_launches                       # the warm-up step and the capture pass are not part of the job
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                  # one eager step: lazy per-kernel initialisation happens outside the capture
-            ws.sc_buf.copy_(self.consts[0])
             pos0, norm0 = b.pos.clone(), b.norm.clone()
-            self.engine.forward(b, ws, ws.sc_buf)
-            self.engine.update(b, ws, ws.sc_buf, *z, no_torsion=no_torsion)
+            sc, trz, rotz, torz = self._step_args(ws, 0, noise_mode)
+            self.engine.forward(b, ws, sc)
+            self.engine.update(b, ws, sc, trz, rotz, torz, no_torsion=no_torsion)
             b.pos.copy_(pos0); b.norm.copy_(norm0)
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
         n0 = ws.n_launches
         with torch.cuda.graph(g):
-            self.engine.forward(b, ws, ws.sc_buf)
-            self.engine.update(b, ws, ws.sc_buf, *z, no_torsion=no_torsion)
+            for k in range(self.steps):
+                sc, trz, rotz, torz = self._step_args(ws, k, noise_mode)
+                self.engine.forward(b, ws, sc)
+                self.engine.update(b, ws, sc, trz, rotz, torz, no_torsion=no_torsion)
         cache[key] = (g, ws.n_launches - n0)
         ws.n_launches = n_before
         b.pos.copy_(pos0); b.norm.copy_(norm0)         # (capture does not execute, but keep the pose exactly as it was)
@@ -149,45 +163,42 @@ class DenoisingSampler:
         """The 20-step loop (sampling.py:204-255) over device-resident chunks; poses end up in each chunk's b.pos.
         pose_trace: optional list; receives per chunk a device tensor [steps + 1, n_lig, 3] = the initial pose and the pose
         after every step (`keep_update`: initial_poses / docked_poses of inference.py:191-192, diffusion_utils.py:71-77)."""
-        dev = self.w.device
         self.engine.timer = timer
         g_off = r_off = 0
         for b, ws, _, _ in resident:
             n0 = ws.n_launches
             sl_g, sl_r = slice(g_off, g_off + b.B), slice(r_off, r_off + b.n_rot)
-            use_graph = self.cuda_graphs and timer is None and trace is None and b.B <= self.graph_max_graphs
-            traj = [b.pos.clone()] if pose_trace is not None else None
-            for k in range(self.steps):
-                sc = self.consts[k]
-                last = k == self.steps - 1
-                if no_random or self.ode or (self.no_final_step_noise and last):
-                    z = (None, None, None)
-                elif noise is None:
-                    z = (torch.randn(b.B, 3, generator=generator, device=dev),
-                         torch.randn(b.B, 3, generator=generator, device=dev),
-                         torch.randn(max(b.n_rot, 1), generator=generator, device=dev))
+            noise_mode = 'none' if (no_random or self.ode) else ('all_but_last' if self.no_final_step_noise else 'all')
+            # ---- all Gaussian draws of the job up front (device RNG, or the injected draws): tr, rot, tor per step
+            if noise_mode != 'none':
+                z_tr, z_rot, z_tor = self._noise_buffers(b, ws)
+                if noise is None:
+                    z_tr.normal_(generator=generator)
+                    z_rot.normal_(generator=generator)
+                    z_tor.normal_(generator=generator)
                 else:
-                    z = tuple(torch.as_tensor(np.asarray(noise[k][key])[s], dtype=torch.float32).contiguous().to(dev)
-                              for key, s in (('tr', sl_g), ('rot', sl_g), ('tor', sl_r)))
-                if use_graph:
-                    graph, n_l = self._step_graph(b, ws, no_torsion, z[0] is not None)
-                    ws.sc_buf.copy_(sc)
-                    if z[0] is not None:
-                        for dst, src in zip(ws.z_buf, z):
-                            dst[:src.shape[0]].copy_(src)       # (the torsion buffer keeps one slot when n_rot = 0)
-                    graph.replay()
-                    ws.n_launches += n_l
+                    for dst, key, sl in ((z_tr, 'tr', sl_g), (z_rot, 'rot', sl_g), (z_tor, 'tor', sl_r)):
+                        host = np.stack([np.asarray(noise[k][key], dtype=np.float32)[sl] for k in range(self.steps)])
+                        if host.size:
+                            dst[:, :host.shape[1]].copy_(torch.from_numpy(host))      # (the torsion buffer keeps one slot when n_rot = 0)
+            use_graph = (self.cuda_graphs and timer is None and trace is None and pose_trace is None
+                         and b.B <= self.graph_max_graphs)
+            if use_graph:
+                graph, n_l = self._loop_graph(b, ws, no_torsion, noise_mode)
+                graph.replay()
+                ws.n_launches += n_l
+            else:
+                traj = [b.pos.clone()] if pose_trace is not None else None
+                for k in range(self.steps):
+                    sc, trz, rotz, torz = self._step_args(ws, k, noise_mode)
+                    self.engine.forward(b, ws, sc)
+                    if trace is not None:
+                        trace.append((ws.tr.clone().cpu(), ws.rot.clone().cpu(), ws.tor[:b.n_rot].clone().cpu()))
+                    self.engine.update(b, ws, sc, trz, rotz, torz, no_torsion=no_torsion)
                     if traj is not None:
                         traj.append(b.pos.clone())
-                    continue
-                self.engine.forward(b, ws, sc)
-                if trace is not None:
-                    trace.append((ws.tr.clone().cpu(), ws.rot.clone().cpu(), ws.tor[:b.n_rot].clone().cpu()))
-                self.engine.update(b, ws, sc, *z, no_torsion=no_torsion)
                 if traj is not None:
-                    traj.append(b.pos.clone())
-            if traj is not None:
-                pose_trace.append(torch.stack(traj))
+                    pose_trace.append(torch.stack(traj))
             self.gpu_launches += ws.n_launches - n0
             g_off += b.B
             r_off += b.n_rot
@@ -195,14 +206,23 @@ class DenoisingSampler:
 
     # ------------------------------------------------------------------ host-facing API
     def run(self, graphs, samples_per_graph=1, noise=None, init=None, no_random=False, generator=None,
-            randomize=True, trace=None, no_torsion=False, pinned=False, keep_update=False):
+            randomize=True, trace=None, no_torsion=False, pinned=False, keep_update=False, start_poses=None):
         """Denoise `samples_per_graph` poses for every pair in `graphs` (host graphs in, host poses out).
 
         init : None (device RNG) or dict(tor=[sum n_rot] , rot=[B,3,3], tr=[B,3]) in graph order (pair-major).
         noise: None (device RNG, or zeros when no_random) or list over steps of dict(tr=[B,3], rot=[B,3], tor=[n_rot]).
+        start_poses: optional (pos, norm) per SAMPLE replacing the pairs' input poses (graph order, pair-major).
         keep_update: also keep the pose after every step; `self.last_trajectory` = CPU tensor [steps + 1, n_lig_total, 3].
         Returns (pos [n_lig_total,3] float32 CPU tensor, lig_ptr numpy [B+1])."""
         resident = self.prepare(graphs, samples_per_graph)
+        if start_poses is not None:
+            # per-SAMPLE start poses (pos [n_lig_total, 3], norm [n_lig_total, 33] in graph order): the callers of the reference
+            # API hand over deep copies of a pair that may already carry different poses
+            o = 0
+            for b, ws, pos0, norm0 in resident:
+                pos0.copy_(torch.as_tensor(start_poses[0][o:o + b.n_lig], dtype=torch.float32))
+                norm0.copy_(torch.as_tensor(start_poses[1][o:o + b.n_lig], dtype=torch.float32).reshape(b.n_lig, 33))
+                o += b.n_lig
         self.reset(resident, generator=generator, init=init, randomize=randomize, no_torsion=no_torsion)
         pose_trace = [] if keep_update else None
         self.run_resident(resident, noise=noise, no_random=no_random, generator=generator, trace=trace, no_torsion=no_torsion,

@@ -283,6 +283,63 @@ def test_reference_facing_api_forward_and_sampling():
     assert model.last_gpu_launches > 0
 
 
+def test_sampling_phore_on_copies_equals_device_side_expansion_and_forward_reuses_the_packed_batch():
+    """The reference hands sampling_phore N deep copies of one pair (inference.py:184).  utils.sampling groups them, uploads the pair
+    once and expands it on the device: the poses must equal DenoisingSampler.run(pair, N) bit for bit (same generator state), the
+    call must not be much slower, and a repeated forward(data) on the same batch must re-use the packed arrays (few launches)."""
+    import time
+    from types import SimpleNamespace
+    from models.score_model_phore import TensorProductScoreModel
+    from utils.sampling import sampling_phore, randomize_position, group_copies
+    from utils.diffusion_utils import set_time_phore, get_t_schedule
+    from diffphore_b200.graph import collate
+    from diffphore_b200.sampler import DenoisingSampler
+    dev = torch.device('cuda:0')
+    model = TensorProductScoreModel(None, dev, None, **SHIPPED_KW)
+    model.load_state_dict(random_state_dict(5), strict=True)
+    model.eval()
+    graphs = load_pairs('synthetic', 2, 20, 6)
+    N, steps = 40, 20
+    sched = get_t_schedule(steps)
+    args = SimpleNamespace(no_torsion=False)
+
+    def api():
+        dl = [g.clone() for g in graphs for _ in range(N)]
+        assert group_copies(dl) is not None and group_copies(dl)[1] == N
+        randomize_position(dl, False, False, 5.0)
+        torch.manual_seed(11)
+        t0 = time.perf_counter()
+        out, _ = sampling_phore(dl, model, steps, sched, sched, sched, dev, None, args, batch_size=N)
+        return torch.cat([g['ligand'].pos for g in out]), time.perf_counter() - t0
+
+    so3n, torn = model.score_norm_tables()
+    smp = DenoisingSampler(model.kernel_weights(dev), steps, so3n, torn)
+
+    def direct():
+        torch.manual_seed(11)
+        t0 = time.perf_counter()
+        pos, _ = smp.run(graphs, N)
+        return pos, time.perf_counter() - t0
+
+    api(); direct()                                                      # warm-up (graph capture, allocator)
+    a, ta = min((api() for _ in range(3)), key=lambda r: r[1])
+    d, td = min((direct() for _ in range(3)), key=lambda r: r[1])
+    assert torch.equal(a, d)
+    print(f'sampling_phore on {2 * N} copies: {1e3 * ta:.1f} ms, DenoisingSampler.run(pairs, {N}): {1e3 * td:.1f} ms')
+    assert ta <= 1.5 * td + 0.02, (ta, td)
+    # forward(data): the second call on the same batch only refreshes positions
+    data = collate([g.clone() for g in graphs])
+    set_time_phore(data, 0.7, 0.7, 0.7, 2, 'cpu')
+    with torch.no_grad():
+        o1 = model(data)
+        n1 = model.last_gpu_launches
+        data['ligand'].pos = data['ligand'].pos + 0.25
+        o2 = model(data)
+        data['ligand'].pos = data['ligand'].pos - 0.25
+        o3 = model(data)
+    assert model.last_gpu_launches == n1 and not torch.equal(o1[0], o2[0]) and all(torch.equal(x, y) for x, y in zip(o1, o3))
+
+
 def test_abi_error_behaviour(built_lib):
     lib = built_lib.load()
     rc = lib.dp_tp_scatter(99, None, None, None, None, 9, None, None, None, None, None, None, 0, 0, 1, None)
@@ -469,7 +526,8 @@ def test_conv_fused_modes_and_split_fallback_for_big_nodes(built_lib):
 
 
 def test_cuda_graph_step_replay_is_bit_identical_to_eager_launches():
-    """Small chunks replay one captured step graph per denoising step (sampler._step_graph); poses must equal eager launches."""
+    """Small chunks replay the whole denoising loop as one captured CUDA graph (sampler._loop_graph); poses must equal eager launches,
+    with injected draws and with the device generator (all draws of a job are made up front in both modes)."""
     from diffphore_b200.engine import ModelWeights
     from diffphore_b200.sampler import DenoisingSampler
     graphs = load_pairs('synthetic', 3, 20, 6)
@@ -484,6 +542,11 @@ def test_cuda_graph_step_replay_is_bit_identical_to_eager_launches():
     d, _ = eager.run(graphs, 2, noise=noise, init=init, no_random=True)
     assert torch.equal(a, b) and torch.equal(c, d) and not torch.equal(a, c)
     assert graph.gpu_launches == eager.gpu_launches
+    dev = torch.device('cuda:0')
+    e, _ = eager.run(graphs, 2, generator=torch.Generator(device=dev).manual_seed(3))
+    f, _ = graph.run(graphs, 2, generator=torch.Generator(device=dev).manual_seed(3))
+    f2, _ = graph.run(graphs, 2, generator=torch.Generator(device=dev).manual_seed(4))
+    assert torch.equal(e, f) and not torch.equal(f, f2)
 
 
 @pytest.mark.parametrize('n_pairs,n_atoms,n_phore,S', [(48, 64, 12, 8), (1, 128, 16, 40)])

@@ -241,18 +241,18 @@ def test_packed_batch_expands_samples_like_a_naive_replication():
     assert a.tiles_cross_lig[2] > 0 and a.tiles_cross_lig[0].shape[0] == a.tiles_cross_lig[2] + 1
 
 
-@pytest.mark.parametrize('layout', ['paths', 'flat', 'flat_trim'])
+@pytest.mark.parametrize('layout', ['paths', 'flat', 'flat_trim', 'gen2'])
 def test_engine_conv_dispatch_follows_the_weight_layout(monkeypatch, layout):
-    """Host glue of Engine._conv (no GPU: the library object is replaced by a recorder): the default layout calls dp_conv_fused
-    with the path-aligned image; DIFFPHORE_W2=flat / flat_trim (experimental) call dp_conv_fused_flat with the flat image and
-    mode bit 4 for the trimmed last chunk."""
+    """Host glue of Engine._conv (no GPU: the library object is replaced by a recorder): DIFFPHORE_W2=paths calls dp_conv_fused with
+    the path-aligned image; flat / flat_trim (the default) call dp_conv_fused_flat with the flat image and mode bit 4 for the
+    trimmed last chunk; the second-generation kernel (default for layer 0 and the torsion convolution, DIFFPHORE_CONV_GEN=2 for
+    all layers) gets the 96-column flat image."""
     from types import SimpleNamespace
     from diffphore_b200.engine import ModelWeights, Engine
-    if layout == 'paths':
-        monkeypatch.delenv('DIFFPHORE_W2', raising=False)
-    else:
-        monkeypatch.setenv('DIFFPHORE_W2', layout)
+    monkeypatch.setenv('DIFFPHORE_W2', 'flat_trim' if layout == 'gen2' else layout)
+    monkeypatch.setenv('DIFFPHORE_CONV_GEN', '2' if layout == 'gen2' else 'auto')
     w = ModelWeights(random_state_dict(0), 'cpu')
+    assert w.convs[('lig', 0)].gen == 2 and w.convs['tor'].gen == 2 and w.convs[('lig', 1)].gen == (2 if layout == 'gen2' else 1)
     eng = Engine(w)
     calls = []
 
@@ -261,9 +261,10 @@ def test_engine_conv_dispatch_follows_the_weight_layout(monkeypatch, layout):
             calls.append((name, a))
             return 0
         return f
-    eng.lib = SimpleNamespace(dp_conv_fused=rec('dp_conv_fused'), dp_conv_fused_flat=rec('dp_conv_fused_flat'))
+    eng.lib = SimpleNamespace(dp_conv_fused=rec('dp_conv_fused'), dp_conv_fused_flat=rec('dp_conv_fused_flat'),
+                              dp_conv_fused2=rec('dp_conv_fused2'))
     cw = w.convs[('lig', 3)]
-    assert (getattr(cw, 'w2imgflat', None) is None) == (layout == 'paths')
+    assert (getattr(cw, 'w2imgflat', None) is None) == (layout in ('paths', 'gen2'))
     z = lambda *s: torch.zeros(*s)
     zi = lambda *s: torch.zeros(*s, dtype=torch.int32)
     ws = SimpleNamespace(n_launches=0)
@@ -272,9 +273,12 @@ def test_engine_conv_dispatch_follows_the_weight_layout(monkeypatch, layout):
               z(3, 100), z(3, 100), 100, 1, 3, 0, 'lig3', tiles)
     (name, a), = calls
     assert ws.n_launches == 1
-    assert name == ('dp_conv_fused' if layout == 'paths' else 'dp_conv_fused_flat')
-    img = cw.w2img112 if layout == 'paths' else cw.w2imgflat
+    assert name == {'paths': 'dp_conv_fused', 'gen2': 'dp_conv_fused2'}.get(layout, 'dp_conv_fused_flat')
+    img = {'paths': cw.w2img112, 'gen2': getattr(cw, 'w2img96', None)}.get(layout, getattr(cw, 'w2imgflat', None))
     as_int = lambda v: v if isinstance(v, int) or v is None else v.value
     assert as_int(a[12]) == img.data_ptr() and a[0] == cw.layer_id
     assert a[27] == (1 | 16 if layout == 'flat_trim' else 1)                      # mode (+ trim bit)
+    if layout == 'gen2':
+        assert img.numel() == 23 * 24576
+        return
     assert img.numel() == (22 if layout == 'paths' else 20) * 28672
