@@ -627,6 +627,9 @@ class Engine:
         # DIFFPHORE_CONV=split: dp_edge_mlp(_tc) -> HBM -> dp_tp_scatter (kept for A/B measurements and as the path for
         # edge sets the fused kernel does not cover: hid != 60, W % 100 != 0, nodes with more than 128 edges)
         self.use_fused = os.environ.get('DIFFPHORE_CONV', 'fused') == 'fused'
+        # see forward(): ligand / pharmacophore convolutions of a layer on two streams (the sampler switches it on for small chunks)
+        self.concurrent = False
+        self.side_stream = torch.cuda.Stream() if weights.device.type == 'cuda' else None
 
     def pack(self, graphs, samples_per_graph=1, wbuf=None):
         """Upload a batch and run the static-geometry setup kernels.  wbuf: optional shared per-edge weight buffer
@@ -712,9 +715,20 @@ class Engine:
             ws.n_launches += 3
             ll_tiles = (ws.ll_tiles, ws.ll_ntiles, ws.ll_tile_cap)
         cv = self.w.convs
+        # Small (latency-bound) batches: the three convolutions that update the pharmacophore nodes of a layer are independent of the
+        # three that update the ligand nodes (both read layer l, write different arrays) -> second stream, joined at the end of
+        # the layer (captured as a fork / join inside the CUDA graphs).  Every output keeps its own order of additions.
+        # The per-edge weight scratch of the unfused fallback is shared, so only the all-fused path may overlap.
+        side = self.side_stream if (self.concurrent and self.timer is None and self.use_fused and b.tiles_cross_lig is not None
+                                    and b.tiles_cross_ph is not None and b.tiles_pp is not None) else None
+        main = torch.cuda.current_stream()
         for l in range(4):
             lh, ph, lo = ws.lig_h[l], ws.ph_h[l] if l < 4 else None, ws.lig_h[l + 1]
             d = LAYER_DIMS[l]
+            st2 = st
+            if l != 3 and side is not None:
+                side.wait_stream(main)
+                st2 = side.cuda_stream
             self._conv(cv[('lig', l)], ws, ws.ll_emb, None, lh, ws.ll_src, lh, ws.ll_dst, None, ws.ll_n, b.ll_cap,
                        lh, ws.ll_dst, ws.ll_sh, 9, ws.ll_ptr, lo, lh, d, 1, b.n_lig, st, f'lig{l}', ll_tiles)
             self._conv(cv[('phore_to_lig', l)], ws, ws.cross_emb, None, lh, b.cross_lig, ph, b.cross_ph, None, None,
@@ -726,13 +740,15 @@ class Engine:
             if l != 3:
                 po = ws.ph_h[l + 1]
                 self._conv(cv[('phore', l)], ws, ws.pp_emb, None, ph, b.pp_src, ph, b.pp_dst, None, None, b.n_pp,
-                           ph, b.pp_dst, ws.pp_sh, 9, b.pp_ptr, po, ph, d, 1, b.n_ph, st, f'pp{l}', b.tiles_pp)
+                           ph, b.pp_dst, ws.pp_sh, 9, b.pp_ptr, po, ph, d, 1, b.n_ph, st2, f'pp{l}', b.tiles_pp)
                 self._conv(cv[('lig_to_phore', l)], ws, ws.cross_emb, b.cross_perm_t, lh, b.cross_lig_t, ph, b.cross_ph_t,
                            None, None, b.n_cross, lh, b.cross_lig_t, ws.cross_sh, 9, b.cross_seg_ph, po, None, 0, 2,
-                           b.n_ph, st, f'l2p{l}', b.tiles_cross_ph)
+                           b.n_ph, st2, f'l2p{l}', b.tiles_cross_ph)
                 self._conv(cv[('lig_to_phore_norm', l)], ws, ws.cross_emb, b.cross_perm_t, lh, b.cross_lig_t, ph,
                            b.cross_ph_t, None, None, b.n_cross, lh, b.cross_lig_t, ws.cross_nsh, 9, b.cross_seg_ph, po,
-                           None, 0, 2, b.n_ph, st, f'l2pn{l}', b.tiles_cross_ph)
+                           None, 0, 2, b.n_ph, st2, f'l2pn{l}', b.tiles_cross_ph)
+                if side is not None:
+                    main.wait_stream(side)
         h4 = ws.lig_h[4]
         L.check(lib.dp_center_step(p(b.pos), p(b.lig_ptr), b.B, sw, scp, p(ws.c_emb), p(ws.c_sh), st), 'dp_center_step')
         self._conv(cv['final'], ws, ws.c_emb, None, h4, b.lig_arange, None, None, None, None, b.n_lig, h4, None, ws.c_sh, 9,

