@@ -55,6 +55,8 @@ class HeteroGraph:
         object.__setattr__(self, '_attrs', {})
 
     def __getitem__(self, key):
+        if isinstance(key, int):                         # PyG Batch[i] (get_example): graph i of a collated batch
+            return uncollate(self)[key]
         key = _EDGE_ALIASES.get(key, key)
         if key not in self._stores:
             self._stores[key] = Store()

@@ -52,6 +52,29 @@ class So3ScoreNorm:
             out[k] = self._rows[int(i)]
         return out
 
+    def score_row(self, i, L=2000, block=250):
+        """_score_norms[i, :] of so3.py:35-43,58: d/d omega log of the IGSO(3) series over the omega grid (cached per row)."""
+        key = ('score', int(i))
+        if key not in self._rows:
+            eps, om = self._eps[i], self._omega
+            p, ds = np.zeros_like(om), np.zeros_like(om)
+            lo, dlo = np.sin(om / 2), 0.5 * np.cos(om / 2)
+            for l0 in range(0, L, block):
+                l = np.arange(l0, min(l0 + block, L))[:, None]
+                w = (2 * l + 1) * np.exp(-l * (l + 1) * eps ** 2)
+                hi = np.sin(om[None] * (l + 0.5))
+                dhi = (l + 0.5) * np.cos(om[None] * (l + 0.5))
+                p += (w * hi / lo[None]).sum(0)
+                ds += (w * (lo[None] * dhi - hi * dlo[None]) / lo[None] ** 2).sum(0)
+            self._rows[key] = ds / p
+        return self._rows[key]
+
+    def score_vec(self, eps, vec):
+        """so3.score_vec (so3.py:84-89): score of the rotation vector `vec` at noise level eps."""
+        i = int(self.index(np.asarray(eps)))
+        om = np.linalg.norm(vec)
+        return np.interp(om, self._omega, self.score_row(i)) * vec / om
+
 
 class TorusScoreNorm:
     def __init__(self, seed=0, n_samples=10000):
@@ -67,12 +90,15 @@ class TorusScoreNorm:
 
     def score_row(self, i):
         """score_[i, :] = grad / p over the x grid with N = 100 images (torus.py:11-22,38-43); NaN where both underflow."""
-        x, sig = self._x, self._sigma[i]
-        k = np.arange(-100, 101)[:, None]
-        xs = x[None] + 2 * np.pi * k
-        e = np.exp(-xs ** 2 / 2 / sig ** 2)
-        with np.errstate(invalid='ignore', divide='ignore'):
-            return (xs / sig ** 2 * e).sum(0) / e.sum(0)
+        key = ('score', int(i))
+        if key not in self._rows:
+            x, sig = self._x, self._sigma[i]
+            k = np.arange(-100, 101)[:, None]
+            xs = x[None] + 2 * np.pi * k
+            e = np.exp(-xs ** 2 / 2 / sig ** 2)
+            with np.errstate(invalid='ignore', divide='ignore'):
+                self._rows[key] = (xs / sig ** 2 * e).sum(0) / e.sum(0)
+        return self._rows[key]
 
     def _row(self, i):
         sig, score_row = self._sigma[i], self.score_row(i)
@@ -91,4 +117,19 @@ class TorusScoreNorm:
             if int(i) not in self._rows:
                 self._rows[int(i)] = self._row(int(i))
             out[k] = self._rows[int(i)]
+        return out
+
+    def score(self, x, sigma):
+        """torus.score (torus.py:46-55): table look-up of the wrapped-normal score of angles x at noise level(s) sigma."""
+        x = np.asarray(x, dtype=np.float64)
+        sigma = np.broadcast_to(np.asarray(sigma, dtype=np.float64), x.shape)
+        x = (x + np.pi) % (2 * np.pi) - np.pi
+        sign = np.sign(x)
+        with np.errstate(divide='ignore'):
+            xi = (np.log(np.abs(x) / np.pi) - np.log(X_MIN)) / (0 - np.log(X_MIN)) * TX_N
+        xi = np.round(np.clip(xi, 0, TX_N)).astype(int)
+        si = self.index(sigma)
+        out = np.empty(x.shape, dtype=np.float64)
+        for k in np.ndindex(x.shape):
+            out[k] = -sign[k] * self.score_row(int(si[k]))[xi[k]]
         return out

@@ -258,24 +258,38 @@ class TensorProductScoreModel(nn.Module):
         t = data.complex_t['tr']
         if not bool((t == t[0]).all()):
             raise NotImplementedError('all graphs of a batch must share one diffusion time (true for sampling_phore)')
-        key = (self._topology_key(data), id(w))
-        cached = self.__dict__.get('_packed')
-        if cached is None or cached[0] != key:
-            from diffphore_b200.graph import uncollate
-            graphs = data.to_data_list() if hasattr(data, 'to_data_list') else uncollate(data)
-            eng = Engine(w)
-            b, ws = eng.pack(graphs, 1)
-            self.__dict__['_packed'] = cached = (key, eng, b, ws)
-        else:                                           # same batch, new pose: only positions and normals travel
-            _, eng, b, ws = cached
+        cached, fresh = self._packed_for(data, w)
+        _, eng, b, ws = cached
+        if not fresh:                                   # same batch, new pose: only positions and normals travel
             b.pos.copy_(data['ligand'].pos.to(torch.float32).reshape(b.n_lig, 3), non_blocking=True)
             b.norm.copy_(data['ligand'].norm.to(torch.float32).reshape(b.n_lig, 33), non_blocking=True)
-        _, eng, b, ws = cached
         n0 = ws.n_launches
         sc = self._step_consts_for(w, float(t[0]))
         tr, rot, tor = eng.forward(b, ws, sc)
         self.last_gpu_launches = ws.n_launches - n0
         return tr.clone(), rot.clone(), tor.clone()
+
+    def _packed_for(self, data, w):
+        """(key, Engine, PackedBatch, Workspace) of a collated batch from a small per-model cache keyed on the batch's topology
+        (a driver alternates between at most a few batches: the graphs of a step and their candidate copies), and whether it was
+        packed just now."""
+        key = (self._topology_key(data), id(w))
+        cache = self.__dict__.setdefault('_packed', {})
+        if key in cache:
+            return cache[key], False
+        from diffphore_b200.graph import uncollate
+        graphs = data.to_data_list() if hasattr(data, 'to_data_list') else uncollate(data)
+        eng = Engine(w)
+        b, ws = eng.pack(graphs, 1)
+        if len(cache) >= 4:
+            cache.pop(next(iter(cache)))
+        cache[key] = (key, eng, b, ws)
+        return cache[key], True
+
+    def _pack_only(self, data):
+        """Pack a collated batch (or re-use the cached packing) without running the score model: for callers that only need the
+        conformer-update kernel on it (utils.sampling.apply_perturbations)."""
+        return self._packed_for(data, self.kernel_weights())[0]
 
     def _step_consts_for(self, w, t):
         """Per-noise-level constant block on the device, cached per t (a sampler visits the same 20 levels again and again)."""

@@ -16,3 +16,8 @@ _table = So3ScoreNorm()
 def score_norm(eps):
     """eps: CPU tensor of rot sigmas -> float32 tensor (same contract as the reference)."""
     return torch.from_numpy(_table(eps.numpy())).float()
+
+
+def score_vec(eps, vec):
+    """Score of a rotation vector at noise level eps (reference so3.py:84-89)."""
+    return _table.score_vec(eps, np.asarray(vec))

@@ -14,3 +14,8 @@ _table = TorusScoreNorm(seed=int(os.environ.get('DIFFPHORE_TORUS_SEED', '0')))
 
 def score_norm(sigma):
     return _table(np.asarray(sigma))
+
+
+def score(x, sigma):
+    """Wrapped-normal score of angles x at noise level sigma (reference torus.py:46-55)."""
+    return _table.score(x, sigma)

@@ -381,3 +381,13 @@ def test_oracle_reproduces_its_frozen_outputs():
             assert float(np.abs(now[k] - gold[k]).max()) <= 1e-3, k          # 20 chained steps (fp32 summation order may differ per host)
         else:
             assert rel(now[k], gold[k]) <= 1e-5, (k, rel(now[k], gold[k]))
+
+
+def test_so3_score_vec_and_torus_score_equal_the_reference_functions():
+    """utils.so3.score_vec (so3.py:84-89) and utils.torus.score (torus.py:46-55) - the training targets of the calibrated sampler
+     - against the reference's own functions evaluated over its own table-building code (tests/golden/tables_ref.npz)."""
+    from utils import so3, torus
+    z = np.load(os.path.join(ROOT, 'tests/golden/tables_ref.npz'))
+    got = np.stack([so3.score_vec(float(e), v) for e, v in zip(z['so3_vec_eps'], z['so3_vec'])])
+    assert np.abs(got - z['so3_score_vec']).max() <= 1e-9 * max(1.0, np.abs(z['so3_score_vec']).max())
+    assert np.allclose(torus.score(z['torus_x'], z['torus_x_sigma']), z['torus_score'], rtol=1e-12, atol=0, equal_nan=True)

@@ -63,6 +63,29 @@ def main():
     with np.errstate(invalid='ignore', divide='ignore'):
         score_rows = np.stack([(tor['grad'](x, sgrid[i], N=100) / tor['p'](x, sgrid[i], N=100))[::25] for i in tidx])
     out.update(torus_sigma=sig, torus_idx=tidx, torus_score_rows=score_rows)
+
+    # ---- so3.score_vec (so3.py:84-89) and torus.score (torus.py:46-55): the reference functions over lazily evaluated table rows
+    class _So3Rows:
+        def __getitem__(self, i):
+            e = so3['_expansion'](omegas, eps_grid[int(i)])
+            return so3['_score'](e, omegas, eps_grid[int(i)])
+    sv = extract(os.path.join(REF, 'so3.py'), {'score_vec'})
+    sv.update(MIN_EPS=MIN_EPS, MAX_EPS=MAX_EPS, N_EPS=N_EPS, _omegas_array=omegas, _score_norms=_So3Rows())
+    rng = np.random.RandomState(5)
+    vecs = rng.randn(4, 3) * np.asarray([[0.05], [0.4], [1.0], [1.7]])
+    veps = np.asarray([0.11, 0.3, 0.8, 1.4])
+    out.update(so3_vec=vecs, so3_vec_eps=veps, so3_score_vec=np.stack([sv['score_vec'](float(e), v) for e, v in zip(veps, vecs)]))
+
+    class _TorusTable:
+        def __getitem__(self, key):
+            si, xi = key
+            with np.errstate(invalid='ignore', divide='ignore'):
+                return np.asarray([(tor['grad'](x, sgrid[int(a)], N=100) / tor['p'](x, sgrid[int(a)], N=100))[int(b)] for a, b in zip(si, xi)])
+    ts = extract(os.path.join(REF, 'torus.py'), {'score'})
+    ts.update(X_MIN=X_MIN, X_N=TX_N, SIGMA_MIN=SIGMA_MIN, SIGMA_MAX=SIGMA_MAX, SIGMA_N=SIGMA_N, score_=_TorusTable())
+    tx = np.asarray([0.3, -1.0, 2.9, -0.002, 4.0])
+    tsg = np.asarray([0.5, 0.05, 2.0, 0.0314, 1.0])
+    out.update(torus_x=tx, torus_x_sigma=tsg, torus_score=ts['score'](tx, tsg))
     path = os.path.join(ROOT, 'tests/golden/tables_ref.npz')
     np.savez_compressed(path, **out)
     print('wrote', path, os.path.getsize(path), 'bytes', {k: v.shape for k, v in out.items()})
