@@ -716,6 +716,14 @@ def test_forward_matches_the_committed_frozen_oracle_outputs(shape):
         for key, val in (('tr', tr), ('rot', rot), ('tor', tor[:b.n_rot])):
             ref = gold[f'{shape}_{tag}{key}']
             assert rel(val.cpu(), ref) <= 1e-4, (shape, tag, key, rel(val.cpu(), ref))
+        if tag == '':
+            # ... the activations after every convolution layer (fp32 oracle) and the float64 evaluation of the same forward
+            acts = dict(act_lig_node_attr1=ws.lig_h[1], act_lig_node_attr2=ws.lig_h[2], act_lig_node_attr3=ws.lig_h[3],
+                        act_lig_node_attr4=ws.lig_h[4], act_final_conv_out=ws.gpred, act_tor_bond_conv_out=ws.tor_feat[:b.n_rot])
+            for key, val in acts.items():
+                assert rel(val.cpu(), gold[f'{shape}_{key}']) <= 1e-4, (shape, key, rel(val.cpu(), gold[f'{shape}_{key}']))
+            for key, val in (('tr', tr), ('rot', rot), ('tor', tor[:b.n_rot])):
+                assert rel(val.cpu().double(), gold[f'{shape}_f64_{key}']) <= 1e-4, (shape, 'f64', key)
 
 
 @pytest.mark.parametrize('layer', [0, 1, 2, 3, 5])

@@ -2,7 +2,8 @@
 tests/golden/oracle_frozen.npz so that an accidental edit of oracle/ (the checker of every GPU parity test) is caught on CPU.
 
     python tools/make_oracle_frozen.py            (no /root/reference needed; deterministic: seeded inputs, seeded weights)
-* forward: tr / rot / tor of the fp32 oracle for one seeded batch of every config shape - cfg1 (real-shaped example pair, P = 79),
+* forward: tr / rot / tor of the fp32 oracle, the activations after every ligand convolution layer / final_conv / tor_bond_conv
+  (act_*), and tr / rot / tor of the same forward in float64 (*_f64_*), for one seeded batch of every config shape - cfg1 (real-shaped example pair, P = 79),
   cfg2 (32 atoms / 8 points), cfg4 (64 / 12), cfg5 (128 / 16) - 2 samples each at t = 0.6, random-init weights (seed 0);
   for cfg1 additionally with the shipped checkpoint when oracle/_ref/weights holds it (skipped otherwise);
 * trajectory: final ligand coordinates of a 20-step run with injected initial poses and noise (2 pairs of 14 atoms / 5 points x 2);
@@ -27,14 +28,22 @@ SHAPES = {'cfg1': ('real', 1, 0, 0), 'cfg2': ('synthetic', 1, 32, 8), 'cfg4': ('
           'cfg5': ('synthetic', 1, 128, 16)}
 
 
-def forward_case(kind, n_pairs, n_atoms, n_phore, sd, so3n, torn, t=0.6, samples=2, seed=3):
+LAYER_KEYS = ('lig_node_attr1', 'lig_node_attr2', 'lig_node_attr3', 'lig_node_attr4', 'final_conv.out', 'tor_bond_conv.out')
+
+
+def forward_case(kind, n_pairs, n_atoms, n_phore, sd, so3n, torn, t=0.6, samples=2, seed=3, dtype=torch.float32, layers=False):
     graphs = load_pairs(kind, n_pairs, n_atoms, n_phore)
     init, _, n_rot = make_draws(graphs, samples, seed)
     dl = oracle_initial_graphs(graphs, samples, init, n_rot)
     batch = collate(dl)
     osamp.set_time(batch, t, len(dl))
+    om = OracleScoreModel(sd, so3n, torn, dtype=dtype)
+    om.trace = {} if layers else None
     with torch.no_grad():
-        return [o.float().numpy() for o in OracleScoreModel(sd, so3n, torn)(batch)]
+        res = [o.double().numpy() if dtype == torch.float64 else o.float().numpy() for o in om(batch)]
+    if layers:                                          # per-convolution-layer activations (SURVEY 8c golden list, item 1)
+        res += [om.trace[k].float().numpy() for k in LAYER_KEYS]
+    return res
 
 
 def trajectory_case(sd, so3n, torn, steps=20, samples=2, seed=11):
@@ -51,8 +60,11 @@ def build():
     out = {}
     sd = random_state_dict(0)
     for name, (kind, n_pairs, n_atoms, n_phore) in SHAPES.items():
-        for key, val in zip(('tr', 'rot', 'tor'), forward_case(kind, n_pairs, n_atoms, n_phore, sd, so3n, torn)):
+        keys = ('tr', 'rot', 'tor') + tuple('act_' + k.replace('.', '_') for k in LAYER_KEYS)
+        for key, val in zip(keys, forward_case(kind, n_pairs, n_atoms, n_phore, sd, so3n, torn, layers=True)):
             out[f'{name}_{key}'] = val
+        for key, val in zip(('tr', 'rot', 'tor'), forward_case(kind, n_pairs, n_atoms, n_phore, sd, so3n, torn, dtype=torch.float64)):
+            out[f'{name}_f64_{key}'] = val              # the same forward evaluated in float64 (noise floor of the fp32 paths)
     if have_checkpoint():
         for key, val in zip(('tr', 'rot', 'tor'), forward_case('real', 1, 0, 0, real_state_dict(), so3n, torn)):
             out[f'cfg1_shipped_{key}'] = val
