@@ -200,11 +200,16 @@ class PoseSink:
 
 
 def plan_jobs(graphs, samples, pairs_cap, graphs_in_flight=4096):
-    """Cross-pair batching: consecutive pairs are grouped into jobs of about `graphs_in_flight`
-    (pair, sample) graphs — enough to fill 148 SMs with 256-edge tile pairs — and never more than `pairs_cap` pairs
-    (what fits the resident HBM budget).  The reference batches only the samples of ONE pair (inference.py:184, sampling.py:210)."""
+    """Cross-pair batching: pairs are BUCKETED by (pharmacophore size, ligand size) - a stable sort, so that a job
+    holds graphs of similar shape: the per-graph kernels (one CTA per graph, sized by the largest ligand of the chunk) and the
+    256-edge pair tiles stay full, and a screening run over one pharmacophore keeps its ligands of equal size together - and then cut
+    into jobs of about `graphs_in_flight` (pair, sample) graphs - enough to fill 148 SMs with 256-edge tile pairs - and never more
+    than `pairs_cap` pairs (what fits the resident HBM budget).  Results are reported in input order (fit re-orders them).
+    The reference batches only the samples of ONE pair (inference.py:184, sampling.py:210)."""
     per_job = max(1, min(pairs_cap, -(-graphs_in_flight // max(1, samples))))
-    return [graphs[k:k + per_job] for k in range(0, len(graphs), per_job)]
+    order = sorted(range(len(graphs)), key=lambda i: (graphs[i]['phore'].pos.shape[0], graphs[i]['ligand'].pos.shape[0]))
+    ordered = [graphs[i] for i in order]
+    return [ordered[k:k + per_job] for k in range(0, len(ordered), per_job)]
 
 
 def fit(args, model, complex_graphs, device, t_to_sigma, tmp_log='', n_report=1000):

@@ -183,10 +183,21 @@ def test_scoring_failure_sentinel_and_job_plan(gold, tmp_path, capsys):
     res = sink.drain()
     sink.close()
     assert [r[0] for r in res] == ['a__b'] and 'x__bad, skipped' in capsys.readouterr().out
-    jobs = inference.plan_jobs(list(range(1000)), 40, pairs_cap=10 ** 6)
-    assert [len(j) for j in jobs][:2] == [103, 103] and sum(len(j) for j in jobs) == 1000 and jobs[-1][-1] == 999
-    assert [len(j) for j in inference.plan_jobs(list(range(7)), 40, pairs_cap=3)] == [3, 3, 1]
-    assert [len(j) for j in inference.plan_jobs(list(range(3)), 10 ** 5, pairs_cap=8)] == [1, 1, 1]
+    import torch
+
+    def fake(n, P, tag):
+        h = HeteroGraph()
+        h['ligand'].pos, h['phore'].pos, h.name = torch.zeros(n, 3), torch.zeros(P, 3), tag
+        return h
+    same = [fake(20, 79, k) for k in range(1000)]
+    jobs = inference.plan_jobs(same, 40, pairs_cap=10 ** 6)
+    assert [len(j) for j in jobs][:2] == [103, 103] and sum(len(j) for j in jobs) == 1000 and jobs[-1][-1].name == 999   # stable: input order kept
+    assert [len(j) for j in inference.plan_jobs(same[:7], 40, pairs_cap=3)] == [3, 3, 1]
+    assert [len(j) for j in inference.plan_jobs(same[:3], 10 ** 5, pairs_cap=8)] == [1, 1, 1]
+    # pairs are bucketed by (pharmacophore size, ligand size): a job holds graphs of similar shape
+    mixed = [fake(n, P, k) for k, (n, P) in enumerate([(30, 79), (14, 8), (31, 79), (14, 79), (15, 8), (29, 79)])]
+    jobs = inference.plan_jobs(mixed, 1, pairs_cap=2, graphs_in_flight=2)
+    assert [[g.name for g in j] for j in jobs] == [[1, 4], [3, 5], [0, 2]]
 
 
 def test_perfect_similarity_matches_the_reference_formula(gold):
@@ -248,7 +259,14 @@ def test_fit_host_logic_jobs_error_isolation_resume_and_keep_update(gold, tmp_pa
     _FakeSampler.poison, _FakeSampler.jobs = ('STL432840',), []
     m = inference.fit(args, model, graphs, 'cpu', None)
     names = [g.name for g in graphs]
-    assert _FakeSampler.jobs == [names[0:2], names[2:4], [names[2]], [names[3]], [names[4]]]   # job 2 failed -> pair by pair
+    by_size = [names[i] for i in sorted(range(5), key=lambda i: graphs[i]['ligand'].pos.shape[0])]      # jobs are bucketed by ligand size
+    planned = [by_size[0:2], by_size[2:4], by_size[4:5]]
+    expect = []
+    for j in planned:                                                                          # the job with the bad pair fails -> pair by pair
+        expect.append(j)
+        if any('STL432840' in n for n in j) and len(j) > 1:
+            expect += [[n] for n in j]
+    assert _FakeSampler.jobs == expect
     assert m['name'] == [n for n in names if 'STL432840' not in n]                             # input order, bad pair skipped
     assert 'STL432840 to the reference pharamcophore, skipped' in capsys.readouterr().out
     assert all(len(f) == 3 for f in m['fitscore']) and len(m['dock_poses'][0]) == 3 and len(m['dock_poses'][0][0]) == 1
@@ -262,7 +280,7 @@ def test_fit_host_logic_jobs_error_isolation_resume_and_keep_update(gold, tmp_pa
         # resume: finished pairs come back from their dock logs, only the skipped pair is attempted again
         _FakeSampler.poison, _FakeSampler.jobs = (), []
         m2 = inference.fit(args, model, graphs, 'cpu', None)
-        assert _FakeSampler.jobs == [[names[2]]] and m2['name'] == names
+        assert _FakeSampler.jobs == [[names[2]]] and m2['name'] == names                       # names[2] = the STL432840 pair
         assert [m2['fitscore'][i] for i in (0, 1, 3, 4)] == m['fitscore']
 
 
