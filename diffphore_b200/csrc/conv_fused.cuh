@@ -39,7 +39,13 @@
 #include "tp_tables.cuh"
 
 #define CF_WORKERS 256
-#define CF_THREADS 352                                // + warps 8, 9: MMA issuers of tile 0 / tile 1, warp 10: TMA producer
+#define CF_THREADS 384                                // + warps 8, 9: MMA issuers of tile 0 / tile 1, warp 10: TMA producer, warp 11: idle
+// Register split (setmaxnreg works per warpgroup, hence the 12th warp): the kernel starts with 168 registers per thread; the
+// auxiliary warpgroup keeps CF_REG_AUX and hands the rest to the two worker warpgroups (256 x 216 + 128 x 72 = 64512 <= 65536).  At
+// 168 the worker loop spilled ~50 accumulator registers per pair tile, and a spill is an L2 round trip here (L1 is ~20 KB next to
+// 227 KB of shared memory and thrashed by the gathers).
+#define CF_REG_WORK 216
+#define CF_REG_AUX 72
 #define CF_CHUNK 100                                  // weight columns per chunk
 #define CF_N 112                                      // MMA N (chunk padded to a multiple of 16)
 #define CF_B_HALF (CF_N * TC_K * 2)                   // one fp16 operand image (hi or lo) of a chunk: 14336 B
@@ -425,7 +431,11 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, *tmem_slot);
 
-    if (warp == 10) {
+    if (warp >= 8) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CF_REG_AUX));
+      if (warp == 11) {
+        // (idle: completes the auxiliary warpgroup)
+      } else if (warp == 10) {
         // ================= TMA producer (one thread): the weight chunks cycle through the ring, pair after pair =================
         if (lane == 0) {
             const uint32_t total_chunks = (uint32_t)my_pairs * (NCH + 1);
@@ -442,7 +452,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
                 }
             }
         }
-    } else if (warp >= 8) {
+      } else {
         // ================= MMA issuers: warp 8 -> tile 0 (accumulator slots 0, 2), warp 9 -> tile 1 (slots 1, 3).
         // One issuing warp needs ~55 clk of instructions per UTCHMMA, about the 56 clk an M=128, N=112, K=16 MMA occupies
         // the tensor pipe, so every barrier round trip of a single issuer would starve the pipe; two issuers hide each
@@ -539,8 +549,10 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
                 }
             }
         }
+      }
     } else {
         // ================= workers: thread = edge =================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CF_REG_WORK));
         const int tile = warp >> 2, wq = warp & 3, row = wq * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
         float* xrow = xs + (size_t)tid * S::XS;
