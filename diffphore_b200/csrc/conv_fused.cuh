@@ -206,6 +206,9 @@ __device__ __forceinline__ void cf_wait3(uint64_t* b0, uint32_t p0, uint64_t* b1
             : "r"(addr), "r"(parity)
             : "memory");
         if (__all_sync(0xffffffffu, ok)) return;
+#ifdef CF_WAIT_BACKOFF
+        if (it >= 4) __nanosleep(32);
+#endif
     }
     __trap();
 }
