@@ -183,7 +183,7 @@ def _make_w1img(w1, b1):
     return img.contiguous().reshape(-1).view(torch.uint8), 2.0 ** (-k)
 
 
-TILE_GROUP = 8      # consecutive graphs whose nodes share one run of tiles (the greedy rule restarts at every group)
+TILE_GROUP = int(os.environ.get('DIFFPHORE_TILE_GROUP', '8'))      # consecutive graphs whose nodes share one run of tiles (the greedy rule restarts at every group)
 
 
 TILE_EDGES = 256    # edges (and nodes) per pair tile of dp_conv_fused: two M = 128 MMA operands
