@@ -41,7 +41,7 @@ def ncu_traffic(tag):
     """dram read + write bytes of the first `tag` launch in the committed ncu --set full summary (None if absent)."""
     try:
         import csv
-        rows = list(csv.reader(open(os.path.join(ROOT, 'profiles', 'ncu_conv_fused_r1_final.csv'))))
+        rows = list(csv.reader(open(os.path.join(ROOT, 'profiles', 'ncu_conv_fused_r2.csv'))))
         h, units = rows[0], rows[1]
         ir, iw = h.index('dram__bytes_read.sum'), h.index('dram__bytes_write.sum')
         scale = {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1.0}

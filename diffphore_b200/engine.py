@@ -668,7 +668,16 @@ class Engine:
                                            p(cw.oscale), p(cw.oshift), p(out), p(residual), res_dim,
                                            mode if flat is None else mode | cw.flat_mode_bits, st), 'dp_conv_fused')
             if tm is not None:
-                tm.stop('conv_fused', name, e0, n_rec, dict(W=cw.W, hid=cw.hid, in_dim=cw.in_dim, d_in=cw.d_in, d_out=cw.d_out,
+                # columns the tensor pipe really multiplies per edge (profiling.roofline_fused: issued MMA work)
+                if getattr(cw, 'gen', 1) == 2:
+                    nch = -(-cw.W // 96)
+                    mma_cols = (nch - 1) * 96 + -(-(cw.W - (nch - 1) * 96) // 16) * 16
+                elif flat is None:
+                    mma_cols = cw.W * 1.12
+                else:
+                    nch = -(-cw.W // 112)
+                    mma_cols = (nch - 1) * 112 + (-(-(cw.W - (nch - 1) * 112) // 16) * 16 if cw.flat_mode_bits else 112)
+                tm.stop('conv_fused', name, e0, n_rec, dict(W=cw.W, hid=cw.hid, in_dim=cw.in_dim, d_in=cw.d_in, d_out=cw.d_out, mma_cols=mma_cols,
                                                             n_out=n_out, tp_flops=cw.tp_flops))
             ws.n_launches += 1
             return

@@ -65,10 +65,10 @@ class KernelTimer:
             for kind, name, sec, E, m in self._resolved():
                 if kind == 'conv_fused' and select(name):
                     f += float(E) * (2.0 * (m['in_dim'] + 1) * m['hid'] + 2.0 * (m['hid'] + 1) * m['W'] + m['tp_flops'])
-                    # columns the tensor pipe really multiplies per edge: W/100 chunks of 112 (path-aligned layout) or
-                    # ceil(W/112) chunks of 112 (experimental flat layout, DIFFPHORE_W2=flat)
-                    layout = os.environ.get('DIFFPHORE_W2', 'paths')
-                    cols = {'flat': -(-m['W'] // 112) * 112, 'flat_trim': -(-m['W'] // 16) * 16}.get(layout, m['W'] * 1.12)
+                    # columns the tensor pipe really multiplies per edge (recorded per launch by Engine._conv: W/100 chunks of 112 for
+                    # the path-aligned layout, consecutive 112- or 96-column chunks with the last one trimmed to a multiple of 16 for
+                    # the flat-trim layouts of the two kernel generations) + the 64 hidden columns, K = 64, three MMAs per product
+                    cols = m.get('mma_cols', m['W'] * 1.12)
                     mma += float(E) * 2.0 * 64 * (cols + 64) * 3
                     b += float(E) * (4 * m['W'] + 4 * m['d_in'] + 4 * 9 + 8) + m['n_out'] * 4 * m['d_out']
                     s += sec
@@ -86,10 +86,10 @@ class KernelTimer:
         out.update(dom)
         out.update(traffic=traffic_bytes, peak_source=f'{peak_src} dense bf16 cuBLAS throughput (sustained)', all_layers=allk,
                    note='achieved = algorithmic FLOPs E*(2*61*60 + 2*61*W + tp_flops) (both MLP layers + channel mixing) / CUDA-event '
-                        'time; the fp32-parity FP16 split issues 3 MMAs per product and pads 100-column chunks to N=112 '
+                        'time; the fp32-parity FP16 split issues 3 MMAs per product over K = 64 (61 used) and the flat-trim chunk layout rounds W up to a multiple of 16 columns '
                         '(issued_mma_*; fp32_parity_bound_frac = algorithmic / issued FLOPs = the largest `frac` this fp32-parity scheme can reach); equiv_hbm_* = bytes the unfused dp_tp_scatter would stream (SURVEY 8d) / this '
                         'kernel\'s time; traffic = dram__bytes_read.sum + dram__bytes_write.sum of this launch in '
-                        'profiles/ncu_conv_fused_r1_final.csv')
+                        'profiles/ncu_conv_fused_r2.csv')
         return out
 
     def roofline(self, peak_gbs, peak_src):
