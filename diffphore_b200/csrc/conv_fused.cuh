@@ -129,7 +129,10 @@ struct ConvFusedSmem {
     static constexpr int X_BYTES = ((256 * ROW_FLOATS * 4 + 127) / 128) * 128;
     static constexpr int TAIL = 2176;                                    // node_seg[257+], oscale/oshift, barriers, tmem slot
     static constexpr int AVAIL = 227 * 1024 - X_BYTES - TAIL - 2 * CF_ALO_TILE;
-    static constexpr int STAGES = AVAIL / CF_B_STAGE > 6 ? 6 : AVAIL / CF_B_STAGE;
+#ifndef CF_MAX_STAGES
+#define CF_MAX_STAGES 6
+#endif
+    static constexpr int STAGES = AVAIL / CF_B_STAGE > CF_MAX_STAGES ? CF_MAX_STAGES : AVAIL / CF_B_STAGE;
     static constexpr int TOTAL = STAGES * CF_B_STAGE + 2 * CF_ALO_TILE + X_BYTES + TAIL;
     static_assert(STAGES >= 3, "weight ring too small");
 };

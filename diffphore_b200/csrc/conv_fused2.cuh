@@ -48,7 +48,10 @@ struct ConvFused2Smem {
     static constexpr int STG_BYTES = 256 * PS * 4;
     static constexpr int TAIL = 6656;                                      // row scales, node_seg (per tile), straddler sums, oscale/oshift, barriers
     static constexpr int AVAIL = 227 * 1024 - 4 * CF_ALO_TILE - X_BYTES - STG_BYTES - TAIL;
-    static constexpr int STAGES = AVAIL / CF2_B_STAGE > 6 ? 6 : AVAIL / CF2_B_STAGE;
+#ifndef CF2_MAX_STAGES
+#define CF2_MAX_STAGES 6
+#endif
+    static constexpr int STAGES = AVAIL / CF2_B_STAGE > CF2_MAX_STAGES ? CF2_MAX_STAGES : AVAIL / CF2_B_STAGE;
     static constexpr int TOTAL = STAGES * CF2_B_STAGE + 4 * CF_ALO_TILE + X_BYTES + STG_BYTES + TAIL;
     static_assert(STAGES >= 3, "weight ring too small");
 };
