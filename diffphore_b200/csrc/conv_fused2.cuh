@@ -39,10 +39,8 @@ struct ConvFused2Smem {
     static constexpr int XCAP = XCAP_RAW > 256 ? 256 : XCAP_RAW;          // rows the window can hold
     static constexpr int X_BYTES = ((XCAP * XS * 4 + 127) / 128) * 128;
     static constexpr int OQ = (Cfg::D_OUT + 3) / 4;                        // float4 quads of an output row
-#ifndef CF2_PQ_BIG
-#define CF2_PQ_BIG 0
-#endif
-    static constexpr int PQ = (CF2_PQ_BIG && OQ > 14) ? 13 : (((OQ + 6) / 7 < (OQ + 4) / 5) ? 7 : 5);       // quads per staged part (odd: conflict-free STS.128 / LDS.128), fewest parts
+    static constexpr int PQ = ((OQ + 6) / 7 < (OQ + 4) / 5) ? 7 : 5;       // quads per staged part (odd: conflict-free STS.128 / LDS.128), fewest parts
+                                                                           // (two parts of 13 quads with a 3-stage ring measured the same)
     static constexpr int NPART = (OQ + PQ - 1) / PQ;
     static constexpr int PS = 4 * PQ;
     static constexpr int STG_BYTES = 256 * PS * 4;
@@ -275,7 +273,7 @@ __global__ void __launch_bounds__(CF2_THREADS, 1) conv_fused2_kernel(ConvFusedAr
              *a_free = bars + 28,        // [buffer][tile]: the pair's last chunk MMA has completed (issuer -> prep)
              *x_ready = bars + 32, *x_free = bars + 33,
              *h_full = bars + 34,        // [tile]: hidden-layer accumulator of the next pair complete (issuer -> prep), one phase per pair
-             *unused_bar = bars + 36;
+             *spare_bar = bars + 36;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 38);
     // parts reduced by tile 0 so far (its partial sums of the straddling node are in smem).  A counter, not an mbarrier: tile 0 is not
     // throttled by tile 1, and a parity wait breaks as soon as the producer runs two phases ahead.
@@ -294,7 +292,7 @@ __global__ void __launch_bounds__(CF2_THREADS, 1) conv_fused2_kernel(ConvFusedAr
             tc_mbar_init(&a1_ready[i], 4); tc_mbar_init(&a2_ready[i], 4); tc_mbar_init(&a_free[i], 1);
         }
         tc_mbar_init(x_ready, 1);
-        tc_mbar_init(unused_bar, 1);
+        tc_mbar_init(spare_bar, 1);
         *strad_cnt = 0;
         tc_mbar_init(&h_full[0], 1);
         tc_mbar_init(&h_full[1], 1);

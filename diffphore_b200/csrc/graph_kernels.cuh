@@ -51,6 +51,40 @@ __device__ __forceinline__ void dp_mlp20_out(const float* h, const float* __rest
     }
 }
 
+// The 20 -> 20 (-> 20) edge-embedding MLPs of the per-edge kernels with the weights TRANSPOSED in shared memory (wt[c * 20 + o]) and
+// packed fp32 FMAs: out pairs (2j, 2j + 1) accumulate x[c] * w[o][c] over c = 0 .. NIN-1 in the same order as the scalar loops they
+// replace (every FFMA2 lane is an IEEE fma: identical results), with one LDS.128 per four weights instead of one LDS per FMA and all
+// accumulators in registers (the scalar version kept h[20] in local memory and ran ~4000 instructions per edge).
+template <int NIN>
+__device__ __forceinline__ void dp_dense20(const float (&x)[NIN], const float* __restrict__ wt, float2 (&acc)[10]) {
+#pragma unroll
+    for (int c = 0; c < NIN; ++c) {
+        if ((c & 1) == 0) asm volatile("" ::: "memory");     // keeps ptxas from hoisting all 5 * NIN weight loads (it spills otherwise)
+        const float2 xc = make_float2(x[c], x[c]);
+        const float4* w4 = reinterpret_cast<const float4*>(wt + c * 20);
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const float4 w = w4[q];
+            acc[2 * q] = __ffma2_rn(xc, make_float2(w.x, w.y), acc[2 * q]);
+            acc[2 * q + 1] = __ffma2_rn(xc, make_float2(w.z, w.w), acc[2 * q + 1]);
+        }
+    }
+}
+// second layer: out = w3 . relu(h) + b3, written as five float4 (rows of the embedding arrays are 80 bytes: 16-byte aligned)
+__device__ __forceinline__ void dp_mlp20_out_t(const float2 (&h2)[10], const float* __restrict__ w3t, const float* __restrict__ b3,
+                                               float* __restrict__ out) {
+    float r[20];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) { r[2 * j] = fmaxf(h2[j].x, 0.f); r[2 * j + 1] = fmaxf(h2[j].y, 0.f); }
+    float2 acc[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) acc[j] = make_float2(b3[2 * j], b3[2 * j + 1]);
+    dp_dense20<20>(r, w3t, acc);
+#pragma unroll
+    for (int q = 0; q < 5; ++q)
+        reinterpret_cast<float4*>(out)[q] = make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // ligand-ligand graph
 // ---------------------------------------------------------------------------------------------------------------
@@ -123,13 +157,15 @@ lig_fill_kernel(const float* __restrict__ pos, const int* __restrict__ lig_ptr, 
                 float* __restrict__ e_emb, float* __restrict__ e_sh) {
     __shared__ float sp[LG_MAXN * 3];
     __shared__ int sthr[LG_MAXN], soff[LG_MAXN + 1];
-    __shared__ float w_rbf[20 * 20], w_bond[20 * 4], w3[20 * 20], b3[20], cst[20];
+    __shared__ __align__(16) float w_rbf[20 * 20], w3[20 * 20];       // transposed: [c][o]
+    __shared__ float w_bond[20 * 4], b3[20], cst[20];
     const int g = blockIdx.x, a0 = lig_ptr[g], n = lig_ptr[g + 1] - a0;
     for (int i = threadIdx.x; i < n * 3; i += blockDim.x) sp[i] = pos[(size_t)a0 * 3 + i];
     for (int i = threadIdx.x; i < n; i += blockDim.x) sthr[i] = thr[a0 + i];
     for (int i = threadIdx.x; i < 400; i += blockDim.x) {
-        w_rbf[i] = sw.lig_edge.w0[(i / 20) * 44 + 24 + (i % 20)];
-        w3[i] = sw.lig_edge.w3[i];
+        const int c = i / 20, o = i % 20;
+        w_rbf[i] = sw.lig_edge.w0[o * 44 + 24 + c];
+        w3[i] = sw.lig_edge.w3[o * 20 + c];
     }
     for (int i = threadIdx.x; i < 80; i += blockDim.x) w_bond[i] = sw.lig_edge.w0[(i / 4) * 44 + (i % 4)];
     for (int i = threadIdx.x; i < 20; i += blockDim.x) { b3[i] = sw.lig_edge.b3[i]; cst[i] = sc[SC_LIG_EDGE + i]; }
@@ -165,16 +201,14 @@ lig_fill_kernel(const float* __restrict__ pos, const int* __restrict__ lig_ptr, 
         const int s = e_src[e] - a0, d = e_dst[e] - a0;
         const int bt = (int)e_sh[(size_t)e * DP_SH];
         const float vx = sp[d * 3] - sp[s * 3], vy = sp[d * 3 + 1] - sp[s * 3 + 1], vz = sp[d * 3 + 2] - sp[s * 3 + 2];
-        float rbf[20], h[20], sh[9];
+        float rbf[20], sh[9];
         dp_rbf20(sqrtf(vx * vx + vy * vy + vz * vz), DP_RBF_LIG, rbf);
-#pragma unroll 4
-        for (int o = 0; o < 20; ++o) {
-            float acc = cst[o] + (bt >= 0 ? w_bond[o * 4 + bt] : 0.f);
+        float2 h2[10];
 #pragma unroll
-            for (int c = 0; c < 20; ++c) acc = fmaf(rbf[c], w_rbf[o * 20 + c], acc);
-            h[o] = acc;
-        }
-        dp_mlp20_out(h, w3, b3, e_emb + (size_t)e * 20);
+        for (int j = 0; j < 10; ++j)
+            h2[j] = make_float2(cst[2 * j] + (bt >= 0 ? w_bond[(2 * j) * 4 + bt] : 0.f), cst[2 * j + 1] + (bt >= 0 ? w_bond[(2 * j + 1) * 4 + bt] : 0.f));
+        dp_dense20<20>(rbf, w_rbf, h2);
+        dp_mlp20_out_t(h2, w3, b3, e_emb + (size_t)e * 20);
         dp_sh9(vx, vy, vz, sh);
 #pragma unroll
         for (int i = 0; i < 9; ++i) e_sh[(size_t)e * DP_SH + i] = sh[i];
@@ -254,12 +288,14 @@ cross_step_kernel(const float* __restrict__ lpos, const float* __restrict__ lnor
                   const float* __restrict__ sc, float* __restrict__ tw_scratch, float* __restrict__ cross_emb,
                   float* __restrict__ cross_sh, float* __restrict__ cross_nsh) {
     extern __shared__ float sden[];        // per-atom softmax denominators
-    __shared__ float w_rbf[20 * 20], w3[20 * 20], b3[20], cst[20], cd_w0[10 * 20], cd_b0[10], cd_w3[10];
+    __shared__ __align__(16) float w_rbf[20 * 20], w3[20 * 20];       // transposed: [c][o]
+    __shared__ float b3[20], cst[20], cd_w0[10 * 20], cd_b0[10], cd_w3[10];
     const int g = blockIdx.x, a0 = lig_ptr[g], n = lig_ptr[g + 1] - a0, p0 = ph_ptr[g], P = ph_ptr[g + 1] - p0;
     const int c0 = cross_ptr[g], ne = n * P;
     for (int i = threadIdx.x; i < 400; i += blockDim.x) {
-        w_rbf[i] = sw.cross_edge.w0[(i / 20) * 73 + 20 + (i % 20)];
-        w3[i] = sw.cross_edge.w3[i];
+        const int c = i / 20, o = i % 20;
+        w_rbf[i] = sw.cross_edge.w0[o * 73 + 20 + c];
+        w3[i] = sw.cross_edge.w3[o * 20 + c];
     }
     for (int i = threadIdx.x; i < 200; i += blockDim.x) cd_w0[i] = sw.cdt.w0[i];
     for (int i = threadIdx.x; i < 20; i += blockDim.x) { b3[i] = sw.cross_edge.b3[i]; cst[i] = sc[SC_CROSS_EDGE + i]; }
@@ -269,16 +305,17 @@ cross_step_kernel(const float* __restrict__ lpos, const float* __restrict__ lnor
     for (int k = threadIdx.x; k < ne; k += blockDim.x) {
         const int a = a0 + k / P, p = p0 + k % P, e = c0 + k;
         const float vx = ppos[p * 3] - lpos[a * 3], vy = ppos[p * 3 + 1] - lpos[a * 3 + 1], vz = ppos[p * 3 + 2] - lpos[a * 3 + 2];
-        float rbf[20], h[20];
+        float rbf[20];
         dp_rbf20(sqrtf(vx * vx + vy * vy + vz * vz), DP_RBF_CROSS, rbf);
-#pragma unroll 4
-        for (int o = 0; o < 20; ++o) {
-            float acc = cst[o] + cross_h[(size_t)e * 20 + o];
+        float2 h2[10];
 #pragma unroll
-            for (int c = 0; c < 20; ++c) acc = fmaf(rbf[c], w_rbf[o * 20 + c], acc);
-            h[o] = acc;
+        for (int q = 0; q < 5; ++q) {
+            const float4 ch = reinterpret_cast<const float4*>(cross_h + (size_t)e * 20)[q];
+            h2[2 * q] = make_float2(cst[4 * q] + ch.x, cst[4 * q + 1] + ch.y);
+            h2[2 * q + 1] = make_float2(cst[4 * q + 2] + ch.z, cst[4 * q + 3] + ch.w);
         }
-        dp_mlp20_out(h, w3, b3, cross_emb + (size_t)e * 20);
+        dp_dense20<20>(rbf, w_rbf, h2);
+        dp_mlp20_out_t(h2, w3, b3, cross_emb + (size_t)e * 20);
         float dsum = sw.cdt.b3[0];
 #pragma unroll 2
         for (int o = 0; o < 10; ++o) {
@@ -465,9 +502,14 @@ tor_fill_kernel(const float* __restrict__ lpos, const int* __restrict__ lig_ptr,
                 int* __restrict__ e_atom, int* __restrict__ e_u, int* __restrict__ e_v, float* __restrict__ e_emb,
                 float* __restrict__ e_sh) {
     __shared__ int soff[LG_MAXN + 1];
-    __shared__ float sw0[400], sw3[400], sb0[20], sb3[20];
+    __shared__ __align__(16) float sw0[400], sw3[400];               // transposed: [c][o]
+    __shared__ float sb0[20], sb3[20];
     const int g = blockIdx.x, a0 = lig_ptr[g], n = lig_ptr[g + 1] - a0, r0 = rot_ptr[g], nr = rot_ptr[g + 1] - r0;
-    for (int i = threadIdx.x; i < 400; i += blockDim.x) { sw0[i] = sw.final_edge.w0[i]; sw3[i] = sw.final_edge.w3[i]; }
+    for (int i = threadIdx.x; i < 400; i += blockDim.x) {
+        const int c = i / 20, o = i % 20;
+        sw0[i] = sw.final_edge.w0[o * 20 + c];
+        sw3[i] = sw.final_edge.w3[o * 20 + c];
+    }
     for (int i = threadIdx.x; i < 20; i += blockDim.x) { sb0[i] = sw.final_edge.b0[i]; sb3[i] = sw.final_edge.b3[i]; }
     if (threadIdx.x == 0) {
         int run = gstart[g];
@@ -499,16 +541,13 @@ tor_fill_kernel(const float* __restrict__ lpos, const int* __restrict__ lig_ptr,
         float b2[9];
         dp_sh9(lpos[v * 3] - lpos[u * 3], lpos[v * 3 + 1] - lpos[u * 3 + 1], lpos[v * 3 + 2] - lpos[u * 3 + 2], b2);   // Y2 = b2[4..8]
         const float vx = lpos[a * 3] - cx, vy = lpos[a * 3 + 1] - cy, vz = lpos[a * 3 + 2] - cz;
-        float rbf[20], h[20], sh[9], o7[8];
+        float rbf[20], sh[9], o7[8];
         dp_rbf20(sqrtf(vx * vx + vy * vy + vz * vz), DP_RBF_LIG, rbf);
-#pragma unroll 4
-        for (int q = 0; q < 20; ++q) {
-            float acc = sb0[q];
+        float2 h2[10];
 #pragma unroll
-            for (int c = 0; c < 20; ++c) acc = fmaf(rbf[c], sw0[q * 20 + c], acc);
-            h[q] = acc;
-        }
-        dp_mlp20_out(h, sw3, sb3, e_emb + (size_t)e * 20);
+        for (int j = 0; j < 10; ++j) h2[j] = make_float2(sb0[2 * j], sb0[2 * j + 1]);
+        dp_dense20<20>(rbf, sw0, h2);
+        dp_mlp20_out_t(h2, sw3, sb3, e_emb + (size_t)e * 20);
         dp_sh9(vx, vy, vz, sh);
         dp_fulltp7(sh, b2 + 4, o7);
         o7[7] = 0.f;
