@@ -49,8 +49,11 @@ __device__ __forceinline__ void cu_axis_angle_to_matrix(float ax, float ay, floa
 __device__ void cu_jacobi3(double* A, double* V) {
     for (int i = 0; i < 9; ++i) V[i] = (i % 4 == 0) ? 1.0 : 0.0;
     for (int sweep = 0; sweep < 30; ++sweep) {
+        // converged once the off-diagonal part is below 1e-18 of the diagonal: further rotations have |s| < 1e-18 and no longer
+        // change a double (the old test, off < 1e-300, ran ~10 sweeps where 5-6 do all the work; this routine is on the
+        // critical path of a CTA, on one thread)
         const double off = A[1] * A[1] + A[2] * A[2] + A[5] * A[5];
-        if (off < 1e-300) break;
+        if (off <= 1e-36 * (A[0] * A[0] + A[4] * A[4] + A[8] * A[8])) break;
         for (int p = 0; p < 2; ++p)
             for (int q = p + 1; q < 3; ++q) {
                 const double apq = A[p * 3 + q];
@@ -106,31 +109,45 @@ __device__ void cu_kabsch_rotation(const double* H, double* R) {
 
 // Sequential torsion moves on the 12N points held in shared memory (pts[0..N) = atoms, pts[N..12N) = norm points,
 // norm point f rides on atom f % N).  theta[r] == 0 skips the bond (torsion.py:83-84).
+// One barrier per bond: every thread builds the bond's rotation matrix itself (same instructions in every lane; the bond's end
+// points u and v are not moved by their own bond - u is on the fixed side, v is the pivot and maps onto itself exactly), the
+// mask row of the NEXT bond is fetched from global memory under the current bond's arithmetic and handed over through
+// shared memory (smask: 2 x n bytes), and the atom a point rides on is tracked incrementally instead of f % n per point.
 __device__ void cu_apply_torsions(float* pts, int n, int nr, const int* __restrict__ rot_u, const int* __restrict__ rot_v,
-                                  const unsigned char* __restrict__ mask, const float* theta, int a0) {
-    __shared__ double Rt[9];
-    __shared__ float pv[3];
+                                  const unsigned char* __restrict__ mask, const float* theta, int a0, unsigned char* smask) {
+    const int step = (int)blockDim.x % n, a_first = (int)threadIdx.x % n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) smask[i] = mask[i];
+    __syncthreads();
     for (int r = 0; r < nr; ++r) {
+        unsigned char* cur = smask + (r & 1) * n;
+        unsigned char* nxt = smask + ((r + 1) & 1) * n;
+        // (a thread owns at most a few atoms' worth of mask bytes: n <= blockDim.x in practice, the loop covers the rest)
+        unsigned char mk = 0;
+        const bool pf = r + 1 < nr && (int)threadIdx.x < n;
+        if (pf) mk = mask[(size_t)(r + 1) * n + threadIdx.x];
         const float th = theta[r];
-        if (th == 0.0f) continue;                 // uniform across the CTA
-        const int u = rot_u[r] - a0, v = rot_v[r] - a0;
-        if (threadIdx.x == 0) {
+        if (th != 0.0f) {                          // uniform across the CTA
+            const int u = rot_u[r] - a0, v = rot_v[r] - a0;
             // rot_vec = (pos[u]-pos[v]) * theta / |pos[u]-pos[v]| in fp32 (numpy), then scipy in fp64
-            float dx = pts[u * 3] - pts[v * 3], dy = pts[u * 3 + 1] - pts[v * 3 + 1], dz = pts[u * 3 + 2] - pts[v * 3 + 2];
-            float nn = sqrtf(dx * dx + dy * dy + dz * dz);
+            const float pvx = pts[v * 3], pvy = pts[v * 3 + 1], pvz = pts[v * 3 + 2];
+            const float dx = pts[u * 3] - pvx, dy = pts[u * 3 + 1] - pvy, dz = pts[u * 3 + 2] - pvz;
+            const float nn = sqrtf(dx * dx + dy * dy + dz * dz);
+            double Rt[9];
             cu_rodrigues((double)(dx * th / nn), (double)(dy * th / nn), (double)(dz * th / nn), Rt);
-            pv[0] = pts[v * 3]; pv[1] = pts[v * 3 + 1]; pv[2] = pts[v * 3 + 2];
-        }
-        __syncthreads();
-        const unsigned char* m = mask + (size_t)r * n;
-        for (int f = threadIdx.x; f < 12 * n; f += blockDim.x) {
-            if (m[f % n]) {
-                const double x = (double)(pts[f * 3] - pv[0]), y = (double)(pts[f * 3 + 1] - pv[1]), z = (double)(pts[f * 3 + 2] - pv[2]);
-                pts[f * 3] = (float)(x * Rt[0] + y * Rt[1] + z * Rt[2] + (double)pv[0]);
-                pts[f * 3 + 1] = (float)(x * Rt[3] + y * Rt[4] + z * Rt[5] + (double)pv[1]);
-                pts[f * 3 + 2] = (float)(x * Rt[6] + y * Rt[7] + z * Rt[8] + (double)pv[2]);
+            int a = a_first;
+            for (int f = threadIdx.x; f < 12 * n; f += blockDim.x) {
+                if (cur[a]) {
+                    const double x = (double)(pts[f * 3] - pvx), y = (double)(pts[f * 3 + 1] - pvy), z = (double)(pts[f * 3 + 2] - pvz);
+                    pts[f * 3] = (float)(x * Rt[0] + y * Rt[1] + z * Rt[2] + (double)pvx);
+                    pts[f * 3 + 1] = (float)(x * Rt[3] + y * Rt[4] + z * Rt[5] + (double)pvy);
+                    pts[f * 3 + 2] = (float)(x * Rt[6] + y * Rt[7] + z * Rt[8] + (double)pvz);
+                }
+                a += step;
+                if (a >= n) a -= n;
             }
         }
+        if (pf) nxt[threadIdx.x] = mk;
+        for (int i = threadIdx.x + blockDim.x; i < n && r + 1 < nr; i += blockDim.x) nxt[i] = mask[(size_t)(r + 1) * n + i];
         __syncthreads();
     }
 }
@@ -139,14 +156,39 @@ __device__ __forceinline__ void cu_load_points(float* pts, const float* __restri
                                                int a0, int n) {
     for (int i = threadIdx.x; i < n * 3; i += blockDim.x) pts[i] = pos[(size_t)a0 * 3 + i];
     __syncthreads();
+    const int step = (int)blockDim.x % n;
+    int a = (int)threadIdx.x % n;
     for (int f = threadIdx.x; f < 11 * n; f += blockDim.x) {          // lig_norm = norm.reshape(-1,N,3) + pos[None]
-        const int a = f % n;
 #pragma unroll
         for (int k = 0; k < 3; ++k) pts[(n + f) * 3 + k] = norm[(size_t)a0 * 33 + (size_t)f * 3 + k] + pts[a * 3 + k];
+        a += step;
+        if (a >= n) a -= n;
     }
     __syncthreads();
 }
+// norm = points - the atom they ride on, back to global memory
+__device__ __forceinline__ void cu_store_norm(const float* pts, float* __restrict__ norm, int a0, int n) {
+    const int step = (int)blockDim.x % n;
+    int a = (int)threadIdx.x % n;
+    for (int f = threadIdx.x; f < 11 * n; f += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) norm[(size_t)a0 * 33 + (size_t)f * 3 + k] = pts[(n + f) * 3 + k] - pts[a * 3 + k];
+        a += step;
+        if (a >= n) a -= n;
+    }
+}
 
+// the centroids of two point sets at once (threads 0-2 and 32-34: two warps, one barrier)
+__device__ __forceinline__ void cu_mean3x2(const float* pa, const float* pb, int n, float* oa, float* ob) {
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (w < 2 && l < 3) {
+        const float* p = w ? pb : pa;
+        float s = 0.f;
+        for (int i = 0; i < n; ++i) s += p[i * 3 + l];
+        (w ? ob : oa)[l] = s / (float)n;
+    }
+    __syncthreads();
+}
 __device__ __forceinline__ void cu_mean3(const float* pts, int n, float* out /*shared[3]*/) {
     if (threadIdx.x < 3) {
         float s = 0.f;
@@ -168,6 +210,7 @@ conformer_update_kernel(float* __restrict__ pos, float* __restrict__ norm, const
     float* pts = smem;                       // [12n][3] current (flexible) points
     float* rigid = pts + 36 * n;             // [n][3] rigid-body positions (Kabsch target)
     float* theta = rigid + 3 * n;            // [nr]
+    unsigned char* smask = reinterpret_cast<unsigned char*>(theta + nr);      // [2][n] mask rows of the bond in flight / the next one
     __shared__ float cen[3], cA[3], cB[3], Rm[9], tr[3], Kr[9], Kt[3];
     __shared__ double Hs[9];
     cu_load_points(pts, pos, norm, a0, n);
@@ -194,10 +237,9 @@ conformer_update_kernel(float* __restrict__ pos, float* __restrict__ norm, const
     }
     __syncthreads();
     if (!no_torsion && nr > 0) {
-        cu_apply_torsions(pts, n, nr, rot_u + r0, rot_v + r0, mask + mask_off[g], theta, a0);
+        cu_apply_torsions(pts, n, nr, rot_u + r0, rot_v + r0, mask + mask_off[g], theta, a0, smask);
         // Kabsch: align flexible (A) onto rigid (B)
-        cu_mean3(pts, n, cA);
-        cu_mean3(rigid, n, cB);
+        cu_mean3x2(pts, rigid, n, cA, cB);
         if (threadIdx.x < 9) {
             const int i = threadIdx.x / 3, j = threadIdx.x % 3;
             float s = 0.f;                                      // H = Am @ Bm^T (fp32 like torch)
@@ -221,11 +263,7 @@ conformer_update_kernel(float* __restrict__ pos, float* __restrict__ norm, const
         __syncthreads();
     }
     for (int i = threadIdx.x; i < n * 3; i += blockDim.x) pos[(size_t)a0 * 3 + i] = pts[i];
-    for (int f = threadIdx.x; f < 11 * n; f += blockDim.x) {
-        const int a = f % n;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) norm[(size_t)a0 * 33 + (size_t)f * 3 + k] = pts[(n + f) * 3 + k] - pts[a * 3 + k];
-    }
+    cu_store_norm(pts, norm, a0, n);
 }
 
 // randomize_position (sampling.py:16-63): random torsions on the input pose, then centre, rotate, translate.
@@ -239,11 +277,12 @@ randomize_position_kernel(float* __restrict__ pos, float* __restrict__ norm, con
     const int g = blockIdx.x, a0 = lig_ptr[g], n = lig_ptr[g + 1] - a0, r0 = rot_ptr[g], nr = rot_ptr[g + 1] - r0;
     float* pts = smem;
     float* theta = pts + 36 * n;
+    unsigned char* smask = reinterpret_cast<unsigned char*>(theta + nr);
     __shared__ float cen[3];
     cu_load_points(pts, pos, norm, a0, n);
     for (int r = threadIdx.x; r < nr; r += blockDim.x) theta[r] = tor_init ? tor_init[r0 + r] : 0.f;
     __syncthreads();
-    if (!no_torsion && nr > 0) cu_apply_torsions(pts, n, nr, rot_u + r0, rot_v + r0, mask + mask_off[g], theta, a0);
+    if (!no_torsion && nr > 0) cu_apply_torsions(pts, n, nr, rot_u + r0, rot_v + r0, mask + mask_off[g], theta, a0, smask);
     // the reference stores norm = points (absolute!) after the torsion pass and only later subtracts: replicate:
     //   pos, norm(abs points) = modify_conformer_torsion_angles(...);  pos' = (pos - c) @ R^T
     //   norm' = (norm_abs.reshape(N,33)... - c) @ R^T - pos'     (sampling.py:50-54)
@@ -256,11 +295,7 @@ randomize_position_kernel(float* __restrict__ pos, float* __restrict__ norm, con
         pts[f * 3 + 2] = x * R[6] + y * R[7] + z * R[8];
     }
     __syncthreads();
-    for (int f = threadIdx.x; f < 11 * n; f += blockDim.x) {
-        const int a = f % n;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) norm[(size_t)a0 * 33 + (size_t)f * 3 + k] = pts[(n + f) * 3 + k] - pts[a * 3 + k];
-    }
+    cu_store_norm(pts, norm, a0, n);
     for (int i = threadIdx.x; i < n * 3; i += blockDim.x)
         pos[(size_t)a0 * 3 + i] = pts[i] + (tr_init ? tr_init[g * 3 + (i % 3)] : 0.f);
 }

@@ -139,9 +139,9 @@ int dp_edge_mlp_tc(const float* emb, const int32_t* perm, const float* tb, const
 int dp_build_tiles(const int32_t* seg_ptr, const int32_t* node_ptr, int32_t n_graphs, int32_t* cnt, int32_t* start,
                    int32_t* tile_node, int32_t* n_tiles_out, void* stream) {
     if (n_graphs <= 0) return DP_OK;
-    tile_count_kernel<<<(n_graphs + 31) / 32, 32, 0, ST(stream)>>>(seg_ptr, node_ptr, n_graphs, cnt);
+    tile_count_kernel<<<(n_graphs * 32 + TILE_WALK_THREADS - 1) / TILE_WALK_THREADS, TILE_WALK_THREADS, 0, ST(stream)>>>(seg_ptr, node_ptr, n_graphs, cnt);
     scan_kernel<<<1, 1024, 0, ST(stream)>>>(cnt, start, n_graphs, n_tiles_out);
-    tile_fill_kernel<<<(n_graphs + 31) / 32, 32, 0, ST(stream)>>>(seg_ptr, node_ptr, n_graphs, start, tile_node);
+    tile_fill_kernel<<<(n_graphs * 32 + TILE_WALK_THREADS - 1) / TILE_WALK_THREADS, TILE_WALK_THREADS, 0, ST(stream)>>>(seg_ptr, node_ptr, n_graphs, start, tile_node);
     return dp_check_launch("dp_build_tiles");
 }
 
@@ -310,7 +310,7 @@ int dp_conformer_update(float* pos, float* norm, const int32_t* lig_ptr, const i
                         const float* tor_score, const float* tr_z, const float* rot_z, const float* tor_z,
                         const float* sc, int32_t no_torsion, void* stream) {
     if (n_graphs <= 0) return DP_OK;
-    const size_t smem = (size_t)(39 * max_atoms + max_rot) * sizeof(float);
+    const size_t smem = (size_t)(39 * max_atoms + max_rot) * sizeof(float) + 2 * (size_t)max_atoms + 16;
     NEED(smem <= 200 * 1024, "dp_conformer_update: ligand too large for shared memory");
     if (smem > 48 * 1024) cudaFuncSetAttribute(conformer_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     conformer_update_kernel<<<n_graphs, CU_THREADS, smem, ST(stream)>>>(
@@ -325,7 +325,7 @@ int dp_randomize_position(float* pos, float* norm, const int32_t* lig_ptr, const
                           const float* tr_init, int32_t no_torsion, void* stream) {
     if (n_graphs <= 0) return DP_OK;
     NEED(rot_init != nullptr, "dp_randomize_position: rot_init missing");
-    const size_t smem = (size_t)(36 * max_atoms + max_rot) * sizeof(float);
+    const size_t smem = (size_t)(36 * max_atoms + max_rot) * sizeof(float) + 2 * (size_t)max_atoms + 16;
     NEED(smem <= 200 * 1024, "dp_randomize_position: ligand too large for shared memory");
     if (smem > 48 * 1024) cudaFuncSetAttribute(randomize_position_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     randomize_position_kernel<<<n_graphs, CU_THREADS, smem, ST(stream)>>>(pos, norm, lig_ptr, rot_ptr, rot_u, rot_v, mask,
