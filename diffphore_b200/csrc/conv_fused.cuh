@@ -893,13 +893,11 @@ __device__ __forceinline__ void tile_walk(const int* __restrict__ seg_ptr, int n
     const int lane = threadIdx.x & 31;
     int fill = 0, nodes = 0;
     bool open = false;
-    int s_cur = seg_ptr[min(n0 + lane, n1)];
+    int s_lo = seg_ptr[min(n0 + lane, n1)], s_hi = seg_ptr[min(n0 + lane + 1, n1)];
     for (int nb = n0; nb < n1; nb += 32) {
-        const int s_nxt = seg_ptr[min(nb + 32 + lane, n1)];                 // next batch: in flight under this one
-        int s_hi = __shfl_down_sync(0xffffffffu, s_cur, 1);
-        const int first_nxt = __shfl_sync(0xffffffffu, s_nxt, 0);
-        if (lane == 31) s_hi = first_nxt;
-        const int deg = s_hi - s_cur;                                        // degree of node nb + lane
+        const int deg = s_hi - s_lo;                                         // degree of node nb + lane
+        s_lo = seg_ptr[min(nb + 32 + lane, n1)];                             // next batch: in flight under this one
+        s_hi = seg_ptr[min(nb + 33 + lane, n1)];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             const int d = __shfl_sync(0xffffffffu, deg, j);
@@ -909,7 +907,6 @@ __device__ __forceinline__ void tile_walk(const int* __restrict__ seg_ptr, int n
                 ++nodes;
             }
         }
-        s_cur = s_nxt;
     }
 }
 #define TILE_WALK_THREADS 128

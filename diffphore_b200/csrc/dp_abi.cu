@@ -51,6 +51,19 @@ int dp_set_constants(const DpConstants* c) {
     return DP_OK;
 }
 
+// CTAs per graph for the per-graph kernels that can share a graph (lig_fill, cross_step, tor_fill): 1 once the graphs alone fill the
+// GPU twice over, up to 8 for small jobs
+static int dp_graph_split(int n_graphs) {
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int s = (2 * n_sm) / (n_graphs > 0 ? n_graphs : 1);
+    return s < 1 ? 1 : (s > 8 ? 8 : s);
+}
+
 int dp_lig_graph(const float* pos, const int32_t* lig_ptr, const int32_t* bond_ptr, const int32_t* bond_dst,
                  const int32_t* bond_type, int32_t n_graphs, int32_t n_lig, int32_t max_atoms,
                  const DpSmallWeights* sw, const float* sc, int32_t* thr, int32_t* deg, int32_t* gcount,
@@ -60,7 +73,7 @@ int dp_lig_graph(const float* pos, const int32_t* lig_ptr, const int32_t* bond_p
     if (n_graphs <= 0) return DP_OK;
     lig_count_kernel<<<n_graphs, LG_THREADS, 0, ST(stream)>>>(pos, lig_ptr, bond_ptr, thr, deg, gcount);
     scan_kernel<<<1, 1024, 0, ST(stream)>>>(gcount, gstart, n_graphs, n_edges_out);
-    lig_fill_kernel<<<n_graphs, LG_THREADS, 0, ST(stream)>>>(pos, lig_ptr, bond_ptr, bond_dst, bond_type, thr, deg, gstart,
+    lig_fill_kernel<<<dim3(n_graphs, dp_graph_split(n_graphs)), LG_THREADS, 0, ST(stream)>>>(pos, lig_ptr, bond_ptr, bond_dst, bond_type, thr, deg, gstart,
                                                             n_graphs, *sw, sc, seg_ptr, e_src, e_dst, e_emb, e_sh);
     return dp_check_launch("dp_lig_graph");
 }
@@ -93,7 +106,7 @@ int dp_cross_step(const float* lpos, const float* lnorm, const float* ppos, cons
                   float* tw_scratch, float* cross_emb, float* cross_sh, float* cross_nsh, void* stream) {
     if (n_graphs <= 0) return DP_OK;
     NEED(max_atoms * sizeof(float) <= 40000, "dp_cross_step: ligand too large");
-    cross_step_kernel<<<n_graphs, CR_THREADS, max_atoms * sizeof(float), ST(stream)>>>(
+    cross_step_kernel<<<dim3(n_graphs, dp_graph_split(n_graphs)), CR_THREADS, max_atoms * sizeof(float), ST(stream)>>>(
         lpos, lnorm, ppos, pnorm, lig_ptr, ph_ptr, cross_ptr, phorefp, phoretype, nangle1, nangle2, cross_h, cross_fm, *sw,
         sc, tw_scratch, cross_emb, cross_sh, cross_nsh);
     return dp_check_launch("dp_cross_step");
@@ -293,7 +306,7 @@ int dp_tor_graph(const float* lpos, const int32_t* lig_ptr, const int32_t* rot_p
     if (n_graphs <= 0 || n_rot <= 0) return DP_OK;
     tor_count_kernel<<<n_graphs, 128, 0, ST(stream)>>>(lpos, lig_ptr, rot_ptr, rot_u, rot_v, deg, gcount);
     scan_kernel<<<1, 1024, 0, ST(stream)>>>(gcount, gstart, n_graphs, n_edges_out);
-    tor_fill_kernel<<<n_graphs, 128, 0, ST(stream)>>>(lpos, lig_ptr, rot_ptr, rot_u, rot_v, deg, gstart, n_graphs, *sw,
+    tor_fill_kernel<<<dim3(n_graphs, dp_graph_split(n_graphs)), 128, 0, ST(stream)>>>(lpos, lig_ptr, rot_ptr, rot_u, rot_v, deg, gstart, n_graphs, *sw,
                                                      seg_ptr, e_atom, e_u, e_v, e_emb, e_sh);
     return dp_check_launch("dp_tor_graph");
 }

@@ -176,11 +176,14 @@ lig_fill_kernel(const float* __restrict__ pos, const int* __restrict__ lig_ptr, 
         soff[n] = run;
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < n; j += blockDim.x) seg_ptr[a0 + j] = soff[j];
-    if (g == n_graphs - 1 && threadIdx.x == 0) seg_ptr[a0 + n] = soff[n];
+    // gridDim.y CTAs share a graph (small jobs: 40 graphs would occupy 40 of 148 SMs): each takes a contiguous range of out nodes
+    const int chunk = (n + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int j_lo = min((int)blockIdx.y * chunk, n), j_hi = min(j_lo + chunk, n);
+    for (int j = j_lo + threadIdx.x; j < j_hi; j += blockDim.x) seg_ptr[a0 + j] = soff[j];
+    if (g == n_graphs - 1 && blockIdx.y == 0 && threadIdx.x == 0) seg_ptr[a0 + n] = soff[n];
     const float r2 = c_dp.lig_radius * c_dp.lig_radius;
     // topology: thread per out node
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    for (int j = j_lo + threadIdx.x; j < j_hi; j += blockDim.x) {
         int o = soff[j];
         for (int b = bond_ptr[a0 + j]; b < bond_ptr[a0 + j + 1]; ++b) {
             e_src[o] = a0 + j; e_dst[o] = bond_dst[b];
@@ -197,7 +200,7 @@ lig_fill_kernel(const float* __restrict__ pos, const int* __restrict__ lig_ptr, 
     }
     __syncthreads();
     // features: thread per edge
-    for (int e = soff[0] + threadIdx.x; e < soff[n]; e += blockDim.x) {
+    for (int e = soff[j_lo] + threadIdx.x; e < soff[j_hi]; e += blockDim.x) {
         const int s = e_src[e] - a0, d = e_dst[e] - a0;
         const int bt = (int)e_sh[(size_t)e * DP_SH];
         const float vx = sp[d * 3] - sp[s * 3], vy = sp[d * 3 + 1] - sp[s * 3 + 1], vz = sp[d * 3 + 2] - sp[s * 3 + 2];
@@ -291,7 +294,11 @@ cross_step_kernel(const float* __restrict__ lpos, const float* __restrict__ lnor
     __shared__ __align__(16) float w_rbf[20 * 20], w3[20 * 20];       // transposed: [c][o]
     __shared__ float b3[20], cst[20], cd_w0[10 * 20], cd_b0[10], cd_w3[10];
     const int g = blockIdx.x, a0 = lig_ptr[g], n = lig_ptr[g + 1] - a0, p0 = ph_ptr[g], P = ph_ptr[g + 1] - p0;
-    const int c0 = cross_ptr[g], ne = n * P;
+    const int c0 = cross_ptr[g];
+    // gridDim.y CTAs share a graph: each takes a contiguous range of ligand atoms with all their P edges
+    const int chunk = (n + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int al_lo = min((int)blockIdx.y * chunk, n), al_hi = min(al_lo + chunk, n);
+    const int k_lo = al_lo * P, ne = al_hi * P;
     for (int i = threadIdx.x; i < 400; i += blockDim.x) {
         const int c = i / 20, o = i % 20;
         w_rbf[i] = sw.cross_edge.w0[o * 73 + 20 + c];
@@ -302,7 +309,7 @@ cross_step_kernel(const float* __restrict__ lpos, const float* __restrict__ lnor
     for (int i = threadIdx.x; i < 10; i += blockDim.x) { cd_b0[i] = sw.cdt.b0[i]; cd_w3[i] = sw.cdt.w3[i]; }
     __syncthreads();
     // pass 1: distance features, edge embedding, total_weight
-    for (int k = threadIdx.x; k < ne; k += blockDim.x) {
+    for (int k = k_lo + threadIdx.x; k < ne; k += blockDim.x) {
         const int a = a0 + k / P, p = p0 + k % P, e = c0 + k;
         const float vx = ppos[p * 3] - lpos[a * 3], vy = ppos[p * 3 + 1] - lpos[a * 3 + 1], vz = ppos[p * 3 + 2] - lpos[a * 3 + 2];
         float rbf[20];
@@ -328,14 +335,14 @@ cross_step_kernel(const float* __restrict__ lpos, const float* __restrict__ lnor
     }
     __syncthreads();
     // per-atom denominator of the 'phore' atom weight (smp:839; no max-subtraction, like the reference)
-    for (int a = threadIdx.x; a < n; a += blockDim.x) {
+    for (int a = al_lo + threadIdx.x; a < al_hi; a += blockDim.x) {
         float s = 0.f;
         for (int p = 0; p < P; ++p) s += expf(tw_scratch[c0 + a * P + p]);
         sden[a] = s;
     }
     __syncthreads();
     // pass 2: gated edge vector SH + angle-matched normal SH
-    for (int k = threadIdx.x; k < ne; k += blockDim.x) {
+    for (int k = k_lo + threadIdx.x; k < ne; k += blockDim.x) {
         const int al = k / P, a = a0 + al, p = p0 + k % P, e = c0 + k;
         const float tw = tw_scratch[e];
         float dir = sw.pdt.b3[0];
@@ -517,11 +524,14 @@ tor_fill_kernel(const float* __restrict__ lpos, const int* __restrict__ lig_ptr,
         soff[nr] = run;
     }
     __syncthreads();
-    for (int r = threadIdx.x; r < nr; r += blockDim.x) seg_ptr[r0 + r] = soff[r];
-    if (g == n_graphs - 1 && threadIdx.x == 0) seg_ptr[r0 + nr] = soff[nr];
+    // gridDim.y CTAs share a graph: each takes a contiguous range of rotatable bonds
+    const int chunk = (nr + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int r_lo = min((int)blockIdx.y * chunk, nr), r_hi = min(r_lo + chunk, nr);
+    for (int r = r_lo + threadIdx.x; r < r_hi; r += blockDim.x) seg_ptr[r0 + r] = soff[r];
+    if (g == n_graphs - 1 && blockIdx.y == 0 && threadIdx.x == 0) seg_ptr[r0 + nr] = soff[nr];
     const float r2 = c_dp.lig_radius * c_dp.lig_radius;
     // topology: thread per rotatable bond (torch_cluster.radius: atoms within 5 A of the bond centre, lowest indices first)
-    for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+    for (int r = r_lo + threadIdx.x; r < r_hi; r += blockDim.x) {
         const int u = rot_u[r0 + r], v = rot_v[r0 + r];
         const float cx = (lpos[u * 3] + lpos[v * 3]) / 2, cy = (lpos[u * 3 + 1] + lpos[v * 3 + 1]) / 2, cz = (lpos[u * 3 + 2] + lpos[v * 3 + 2]) / 2;
         int o = soff[r], d = 0;
@@ -535,7 +545,7 @@ tor_fill_kernel(const float* __restrict__ lpos, const int* __restrict__ lig_ptr,
     }
     __syncthreads();
     // features: thread per edge (the 20 -> 20 -> 20 embedding MLP dominates; all 128 threads busy instead of one per bond)
-    for (int e = soff[0] + threadIdx.x; e < soff[nr]; e += blockDim.x) {
+    for (int e = soff[r_lo] + threadIdx.x; e < soff[r_hi]; e += blockDim.x) {
         const int a = e_atom[e], u = e_u[e], v = e_v[e];
         const float cx = (lpos[u * 3] + lpos[v * 3]) / 2, cy = (lpos[u * 3 + 1] + lpos[v * 3 + 1]) / 2, cz = (lpos[u * 3 + 2] + lpos[v * 3 + 2]) / 2;
         float b2[9];
