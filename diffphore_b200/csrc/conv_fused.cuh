@@ -878,54 +878,61 @@ static int conv_fused_launch(const ConvFusedArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------------------------
 // Tile builder for dynamic graphs: greedy node-aligned packing (<= 256 edges and <= 256 nodes per pair tile), restarted at every GROUP of
 // graphs (node_ptr holds the first node of every group; the engine groups 8 consecutive graphs) so that groups can be
-// processed in parallel (one thread per group), two passes around the exclusive scan.  Tiles may span graphs: a row of
+// processed in parallel, two passes around the exclusive scan.  Tiles may span graphs: a row of
 // the M = 128 MMA operand is one edge and rows are independent, so the per-node sums do not depend on the tiling
 // (bit-identical, tested); restarting at every graph instead left the last tile of every graph mostly empty
 // (cfg2: 5.2 -> 4.8 ligand-ligand M=128 operands, 3.8 -> 3.4 torsion operands per graph).  The node cap bounds node_seg[] in
-// shared memory (zero-degree nodes ride along with their neighbours).  The degrees of 8 nodes are loaded
-// together: the greedy rule is sequential, the loads are not.
+// shared memory (zero-degree nodes ride along with their neighbours).
 // ---------------------------------------------------------------------------------------------------------------
-// One WARP per group: the lanes load 32 consecutive seg_ptr entries at once (and the next 32 while the current ones are
-// consumed), the greedy rule itself runs redundantly in every lane on shuffled degrees.  (A single thread per group with 8-node
-// load batches was latency bound: 59 + 72 us per build for the 5 groups of a 40-graph job, 10 % of its step.)
+// One CTA per group.  The greedy rule is sequential over NODES (~100 clk per node on one thread or one warp: 50-70 us per build
+// for the 1024-node groups of a 40-graph job, 10 % of its step), but the tile that STARTS at node i is a function of i alone: it ends
+// before nxt(i) = the first j > i with seg[j + 1] - seg[i] > 256 or j - i == 256.  All nxt(i) are found in parallel (binary search
+// in the monotone seg_ptr, L1-resident), then one thread hops from tile start to tile start through shared memory: sequential
+// over TILES only.  Groups beyond TILE_WALK_CAP nodes fall back to the node-by-node walk.
+#define TILE_WALK_THREADS 128
+#define TILE_WALK_CAP 4096
 template <class F>
-__device__ __forceinline__ void tile_walk(const int* __restrict__ seg_ptr, int n0, int n1, F&& on_tile) {
-    const int lane = threadIdx.x & 31;
-    int fill = 0, nodes = 0;
-    bool open = false;
-    int s_lo = seg_ptr[min(n0 + lane, n1)], s_hi = seg_ptr[min(n0 + lane + 1, n1)];
-    for (int nb = n0; nb < n1; nb += 32) {
-        const int deg = s_hi - s_lo;                                         // degree of node nb + lane
-        s_lo = seg_ptr[min(nb + 32 + lane, n1)];                             // next batch: in flight under this one
-        s_hi = seg_ptr[min(nb + 33 + lane, n1)];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int d = __shfl_sync(0xffffffffu, deg, j);
-            if (nb + j < n1) {
-                if (!open || fill + d > 256 || nodes == 256) { on_tile(nb + j); fill = 0; nodes = 0; open = true; }
-                fill += d;
-                ++nodes;
+__device__ __forceinline__ void tile_walk(const int* __restrict__ seg_ptr, int n0, int n1, int* nxt /*shared[TILE_WALK_CAP]*/, F&& on_tile) {
+    const int cnt = n1 - n0;
+    if (cnt <= TILE_WALK_CAP) {
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+            const int s_i = seg_ptr[n0 + i];
+            int lo = i + 1, hi = min(i + 256, cnt);
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (seg_ptr[n0 + mid + 1] - s_i > 256) hi = mid; else lo = mid + 1;
             }
+            nxt[i] = lo;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int t = 0; t < cnt; t = nxt[t]) on_tile(n0 + t);
+    } else if (threadIdx.x == 0) {
+        int fill = 0, nodes = 0;
+        bool open = false;
+        for (int i = n0; i < n1; ++i) {
+            const int d = seg_ptr[i + 1] - seg_ptr[i];
+            if (!open || fill + d > 256 || nodes == 256) { on_tile(i); fill = 0; nodes = 0; open = true; }
+            fill += d;
+            ++nodes;
         }
     }
 }
-#define TILE_WALK_THREADS 128
 __global__ void __launch_bounds__(TILE_WALK_THREADS)
 tile_count_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ node_ptr, int n_groups, int* __restrict__ cnt) {
-    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;            // warp-uniform
-    if (g >= n_groups) return;
+    __shared__ int nxt[TILE_WALK_CAP];
+    const int g = blockIdx.x;
     int tiles = 0;
-    tile_walk(seg_ptr, node_ptr[g], node_ptr[g + 1], [&](int) { ++tiles; });
-    if ((threadIdx.x & 31) == 0) cnt[g] = tiles;
+    tile_walk(seg_ptr, node_ptr[g], node_ptr[g + 1], nxt, [&](int) { ++tiles; });
+    if (threadIdx.x == 0) cnt[g] = tiles;
 }
 __global__ void __launch_bounds__(TILE_WALK_THREADS)
 tile_fill_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ node_ptr, int n_groups,
                  const int* __restrict__ start, int* __restrict__ tile_node) {
-    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (g >= n_groups) return;
+    __shared__ int nxt[TILE_WALK_CAP];
+    const int g = blockIdx.x;
     const int n1 = node_ptr[g + 1];
-    const bool writer = (threadIdx.x & 31) == 0;
     int t = start[g];
-    tile_walk(seg_ptr, node_ptr[g], n1, [&](int n) { if (writer) tile_node[t] = n; ++t; });
-    if (writer && g == n_groups - 1) tile_node[start[n_groups]] = n1;     // sentinel: one past the last node
+    tile_walk(seg_ptr, node_ptr[g], n1, nxt, [&](int n) { tile_node[t++] = n; });
+    if (threadIdx.x == 0 && g == n_groups - 1) tile_node[start[n_groups]] = n1;     // sentinel: one past the last node
 }

@@ -152,9 +152,9 @@ int dp_edge_mlp_tc(const float* emb, const int32_t* perm, const float* tb, const
 int dp_build_tiles(const int32_t* seg_ptr, const int32_t* node_ptr, int32_t n_graphs, int32_t* cnt, int32_t* start,
                    int32_t* tile_node, int32_t* n_tiles_out, void* stream) {
     if (n_graphs <= 0) return DP_OK;
-    tile_count_kernel<<<(n_graphs * 32 + TILE_WALK_THREADS - 1) / TILE_WALK_THREADS, TILE_WALK_THREADS, 0, ST(stream)>>>(seg_ptr, node_ptr, n_graphs, cnt);
+    tile_count_kernel<<<n_graphs, TILE_WALK_THREADS, 0, ST(stream)>>>(seg_ptr, node_ptr, n_graphs, cnt);
     scan_kernel<<<1, 1024, 0, ST(stream)>>>(cnt, start, n_graphs, n_tiles_out);
-    tile_fill_kernel<<<(n_graphs * 32 + TILE_WALK_THREADS - 1) / TILE_WALK_THREADS, TILE_WALK_THREADS, 0, ST(stream)>>>(seg_ptr, node_ptr, n_graphs, start, tile_node);
+    tile_fill_kernel<<<n_graphs, TILE_WALK_THREADS, 0, ST(stream)>>>(seg_ptr, node_ptr, n_graphs, start, tile_node);
     return dp_check_launch("dp_build_tiles");
 }
 
