@@ -183,7 +183,17 @@ def _make_w1img(w1, b1):
     return img.contiguous().reshape(-1).view(torch.uint8), 2.0 ** (-k)
 
 
-TILE_GROUP = int(os.environ.get('DIFFPHORE_TILE_GROUP', '8'))      # consecutive graphs whose nodes share one run of tiles (the greedy rule restarts at every group)
+# Consecutive graphs whose nodes share one run of tiles (the greedy rule restarts at every group, the half-empty last tile of
+# a group is the cost).  'auto': ~1024 ligand atoms per group (32 graphs at 32 atoms, 8 at 128) - the device-side builder works
+# a group per CTA and falls back to a sequential walk beyond 4096 nodes (conv_fused.cuh, TILE_WALK_CAP).
+_TILE_GROUP_ENV = os.environ.get('DIFFPHORE_TILE_GROUP', 'auto')
+TILE_GROUP = 8 if _TILE_GROUP_ENV == 'auto' else int(_TILE_GROUP_ENV)
+
+
+def tile_group_for(n_atoms, n_graphs):
+    if _TILE_GROUP_ENV != 'auto':
+        return TILE_GROUP
+    return int(min(64, max(1, 1024 // max(1, -(-n_atoms // max(1, n_graphs))))))
 
 
 TILE_EDGES = 256    # edges (and nodes) per pair tile of dp_conv_fused: two M = 128 MMA operands
@@ -474,9 +484,10 @@ class PackedBatch:
         a0, p0 = atoms.gbase, phs.gbase                                # first atom / phore node of every graph
         self.lig_ptr, self.ph_ptr, self.rot_ptr = i32(a0), i32(p0), i32(rots.gbase)
         # first atom / rotatable bond of every group of TILE_GROUP graphs (+ total): restart points of dp_build_tiles
-        self.n_groups = (B + TILE_GROUP - 1) // TILE_GROUP
-        self.lig_gptr = i32(torch.cat([a0[:-1:TILE_GROUP], a0[-1:]]))
-        self.rot_gptr = i32(torch.cat([rots.gbase[:-1:TILE_GROUP], rots.gbase[-1:]]))
+        G = self.tile_group = tile_group_for(int(np.sum(n_p)) * S, B)
+        self.n_groups = (B + G - 1) // G
+        self.lig_gptr = i32(torch.cat([a0[:-1:G], a0[-1:]]))
+        self.rot_gptr = i32(torch.cat([rots.gbase[:-1:G], rots.gbase[-1:]]))
         self.lig_batch = i32(atoms.graph)
         # ---- bonds (CSR by source atom), rotatable bonds, phore-phore edges (CSR by source node)
         bptr_c = cat_ptr = up(np.concatenate([q.bond_ptr[:-1] for q in pa]).astype(np.int64))
@@ -524,7 +535,7 @@ class PackedBatch:
             if n_t == 0 or n_e >= 0.95 * cap_edges * n_t:
                 return tiles(per_pair, node_base, n_nodes)
             deg = np.concatenate([np.tile(np.asarray(d, np.int64), S) for d in deg_pair])
-            tn = grouped_tiles(deg, np.repeat(nodes_pair, S))
+            tn = grouped_tiles(deg, np.repeat(nodes_pair, S), group=self.tile_group)
             return (i32(torch.cat([up(tn), torch.full((1,), n_nodes, **i64)])), None, len(tn))
 
         cap_edges = TILE_EDGES
