@@ -31,7 +31,7 @@ def random_rotations(n, generator=None, device='cpu'):
 class DenoisingSampler:
     def __init__(self, weights: ModelWeights, inference_steps=20, so3_norm=None, torus_norm=None,
                  weight_buffer_bytes=24 << 30, no_final_step_noise=False, resident_bytes=48 << 30,
-                 cuda_graphs=True, graph_max_graphs=2048, ode=False):
+                 cuda_graphs=True, graph_max_graphs=2048, ode=False, pipeline_graphs=None, pipeline_head_graphs=640):
         self.w = weights
         self.engine = Engine(weights)
         self.steps = inference_steps
@@ -39,6 +39,15 @@ class DenoisingSampler:
         self.torus = torus_norm or TorusScoreNorm()
         self.weight_buffer_bytes = weight_buffer_bytes
         self.resident_bytes = resident_bytes
+        # run(): optional cap on the graphs (pair x sample) per chunk of a one-shot job.  Jobs that need several chunks anyway are
+        # pipelined (chunk k+1 packed / uploaded under chunk k's kernels); cutting a job that fits one chunk just to pipeline it
+        # does not pay: measured on cfg2 (10240 graphs), 3 chunks hide 19 of the 29 ms of packing but add 1720 launches of
+        # ~15-20 us fixed cost each (0.759 s vs 0.756 s per job) - hence None.
+        self.pipeline_graphs = pipeline_graphs
+        # ... but a SHORT head chunk does: 640 graphs (16 cfg2 pairs, 2 ms of packing) keep the GPU busy for ~50 ms while the host
+        # packs the bulk of the job; one extra set of 860 launches.  Measured on cfg2: 0.751 -> 0.744 s per job (+1 %); 320 / 1280
+        # graphs: 0.745 / 0.754 s.  0 disables it.
+        self.pipeline_head_graphs = pipeline_head_graphs
         # resident chunks that are denoised repeatedly replay their whole loop as one captured CUDA graph (see _loop_graph)
         self.cuda_graphs, self.graph_max_graphs = cuda_graphs, graph_max_graphs
         self.no_final_step_noise = no_final_step_noise
@@ -209,6 +218,47 @@ class DenoisingSampler:
         self.engine.timer = None
         self.engine.concurrent = False
 
+    def _run_pipelined(self, graphs, samples_per_graph, bounds, no_random, generator, randomize, no_torsion, pinned):
+        """run() for jobs of several chunks with device-side draws: chunk k+1 is packed on the host and uploaded on a copy
+        stream while the GPU denoises chunk k (the 860 launches of a chunk take ~10 ms of host time, its kernels ~250 ms), so
+        only the first chunk's packing is exposed.  Same kernels and per-chunk results as the plain path; the random streams
+        are consumed chunk by chunk (initial poses, then noise) instead of all initial poses first."""
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.w.device)
+        compute = torch.cuda.current_stream()
+        self.last_h2d_bytes, wbuf = 0, None
+
+        def pack(i):
+            nonlocal wbuf
+            with torch.cuda.stream(self._copy_stream):
+                b, ws = self.engine.pack(graphs[bounds[i]:bounds[i + 1]], samples_per_graph, wbuf)
+                wbuf = ws.wbuf if wbuf is None or ws.wbuf.numel() > wbuf.numel() else wbuf
+                item = (b, ws, b.pos.clone(), b.norm.clone())
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            self.last_h2d_bytes += b.h2d_bytes
+            return item, ev
+
+        resident, nxt, n_chunks = [], pack(0), len(bounds) - 1
+        for i in range(n_chunks):
+            item, ev = nxt
+            compute.wait_event(ev)
+            self.reset([item], generator=generator, randomize=randomize, no_torsion=no_torsion)
+            self.run_resident([item], no_random=no_random, generator=generator, no_torsion=no_torsion, whole_loop=False)
+            resident.append(item)
+            if i + 1 < n_chunks:
+                nxt = pack(i + 1)                           # host work and H2D of the next chunk, under this chunk's kernels
+        self.last_trajectory = None
+        n_tot = sum(b.n_lig for b, _, _, _ in resident)
+        out = torch.empty(n_tot, 3, dtype=torch.float32, pin_memory=pinned)
+        ptr, o = [0], 0
+        for b, ws, _, _ in resident:
+            out[o:o + b.n_lig].copy_(b.pos, non_blocking=pinned)
+            o += b.n_lig
+            ptr += (np.cumsum(b.n_per) + ptr[-1]).tolist()
+        torch.cuda.synchronize()
+        return out, np.asarray(ptr)
+
     # ------------------------------------------------------------------ host-facing API
     def run(self, graphs, samples_per_graph=1, noise=None, init=None, no_random=False, generator=None,
             randomize=True, trace=None, no_torsion=False, pinned=False, keep_update=False, start_poses=None):
@@ -219,6 +269,20 @@ class DenoisingSampler:
         start_poses: optional (pos, norm) per SAMPLE replacing the pairs' input poses (graph order, pair-major).
         keep_update: also keep the pose after every step; `self.last_trajectory` = CPU tensor [steps + 1, n_lig_total, 3].
         Returns (pos [n_lig_total,3] float32 CPU tensor, lig_ptr numpy [B+1])."""
+        chunk = self.graphs_per_chunk(graphs, samples_per_graph)
+        if start_poses is None and init is None and noise is None and trace is None and not keep_update:
+            # one-shot job with device-side draws: when it takes several chunks, packing / upload of chunk k+1 overlaps the kernels
+            # of chunk k
+            if self.pipeline_graphs:
+                n_chunks = max(-(-len(graphs) // chunk), -(-len(graphs) * samples_per_graph // self.pipeline_graphs))
+                chunk = -(-len(graphs) // n_chunks)
+            bounds = list(range(0, len(graphs), chunk)) + [len(graphs)]
+            # a short head chunk gets the GPU going while the host packs the bulk of the job
+            head = self.pipeline_head_graphs // max(1, samples_per_graph)
+            if head and bounds[1] > 8 * head:
+                bounds.insert(1, head)
+            if len(bounds) > 2:
+                return self._run_pipelined(graphs, samples_per_graph, bounds, no_random, generator, randomize, no_torsion, pinned)
         resident = self.prepare(graphs, samples_per_graph)
         if start_poses is not None:
             # per-SAMPLE start poses (pos [n_lig_total, 3], norm [n_lig_total, 33] in graph order): the callers of the reference
