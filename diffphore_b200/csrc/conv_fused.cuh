@@ -748,9 +748,10 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_fused_kernel(ConvFusedArgs
             const uint32_t item0 = item;
             Idx nx = ix;
             if constexpr (FLAT) {
-                cf_flat_chunks<Cfg, 0, 4>(lane_base, t_full, t_empty, item, tile, xrow, shv, acc, lane);
+                constexpr int CS = NCH < 4 ? NCH : 4;                    // (final_conv has two chunks)
+                cf_flat_chunks<Cfg, 0, CS>(lane_base, t_full, t_empty, item, tile, xrow, shv, acc, lane);
                 if (pi + 1 < my_pairs) nx = fetch(pair + (int)gridDim.x);
-                cf_flat_chunks<Cfg, 4, NCH>(lane_base, t_full, t_empty, item, tile, xrow, shv, acc, lane);
+                cf_flat_chunks<Cfg, CS, NCH>(lane_base, t_full, t_empty, item, tile, xrow, shv, acc, lane);
             } else {
                 cf_paths<Cfg, 0, 1, PROBE>(lane_base, t_full, t_empty, item, tile, ntile, active, xrow, shv, acc, lane, pi == 1, item0, a_dbg);
                 if (pi + 1 < my_pairs) nx = fetch(pair + (int)gridDim.x);

@@ -189,6 +189,7 @@ static int conv_fused_dispatch(bool flat, int32_t layer, const float* emb, const
             case DP_TP_L2: return conv_fused_launch<CfFlatTrim<TpL2>>(a, ST(stream));
             case DP_TP_L3: return conv_fused_launch<CfFlatTrim<TpL3>>(a, ST(stream));
             case DP_TP_TOR: return conv_fused_launch<CfFlatTrim<TpTor>>(a, ST(stream));
+            case DP_TP_FINAL: return conv_fused_launch<CfFlatTrim<TpFinal>>(a, ST(stream));   /* fc 40 -> 40 -> 200 zero padded to 60 / 60 */
         }
         dp_set_error("dp_conv_fused_flat: unsupported layer %d", layer);
         return DP_ERR_ARG;

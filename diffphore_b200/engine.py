@@ -82,6 +82,20 @@ class ConvWeights:
                     self.flat_mode_bits = 16 if layout == 'flat_trim' else 0      # bit 4 of `mode`: last chunk's MMA trimmed
                 img, self.inv_w1scale = _make_w1img(_f32(sd[prefix + '.fc.0.weight']).cpu(), _f32(sd[prefix + '.fc.0.bias']).cpu())
                 self.w1img = img.to(device)
+        elif self.hid == 40 and self.in_dim == 40 and layer_id == L.TP_FINAL and os.environ.get('DIFFPHORE_FINAL', 'fused') == 'fused':
+            # final_conv (fc 40 -> 40 -> 200, attributes [centre-edge embedding | atom scalars]) on the fused kernel: both MLP
+            # layers zero padded to the kernel's 60 / 60 (the padded hidden units are ReLU(0) = 0; the kernel's third attribute
+            # block re-reads the atom scalars against zero weights, so the operand scale - the row maximum - is unchanged)
+            w1p, b1p = torch.zeros(60, 60), torch.zeros(60)
+            w1p[:40, :40] = _f32(sd[prefix + '.fc.0.weight']).cpu()
+            b1p[:40] = _f32(sd[prefix + '.fc.0.bias']).cpu()
+            w3p = torch.zeros(numel, 60)
+            w3p[:, :40] = _f32(w3).cpu()
+            img, self.inv_wscale = _make_w2imgflat(w3p, _f32(sd[prefix + '.fc.3.bias']).cpu())
+            self.w2imgflat = self.w2img112 = img.to(device)                  # (w2img112: the fused path's "images present" marker)
+            self.flat_mode_bits, self.gen = 16, 1
+            img, self.inv_w1scale = _make_w1img(w1p, b1p)
+            self.w1img = img.to(device)
         # eval BatchNorm (e3nn.nn.BatchNorm) and path weights folded into per-component scale/shift
         bw, bb = sd[prefix + '.batch_norm.weight'].double(), sd[prefix + '.batch_norm.bias'].double()
         rm, rv = sd[prefix + '.batch_norm.running_mean'].double(), sd[prefix + '.batch_norm.running_var'].double()
@@ -542,6 +556,9 @@ class PackedBatch:
         self.tiles_cross_lig = tiles_any(t_lig, a0, self.n_lig, [np.full(q.n, q.P) for q in pa], n_p)
         self.tiles_cross_ph = tiles_any(t_ph, p0, self.n_ph, [np.full(q.P, q.n) for q in pa], P_p)
         self.tiles_pp = tiles_any(t_pp, p0, self.n_ph, [np.diff(q.pp_ptr) for q in pa], P_p)
+        # final_conv: one edge per atom to its graph's centre node -> output nodes = graphs, degree = atoms of the graph
+        tn = grouped_tiles(np.repeat(n_p, S), np.ones(B, np.int64), group=64)
+        self.tiles_final = None if tn is None else (i32(torch.cat([up(tn), torch.full((1,), B, **i64)])), None, len(tn))
         # ---- mask_rotate rows (uint8) and their per-graph byte offsets
         msk = Level(nrot_p * n_p)
         self.mask = up(np.concatenate([q.mask.reshape(-1) for q in pa]).astype(np.uint8))[msk.src].contiguous() \
@@ -771,8 +788,12 @@ class Engine:
                     main.wait_stream(side)
         h4 = ws.lig_h[4]
         L.check(lib.dp_center_step(p(b.pos), p(b.lig_ptr), b.B, sw, scp, p(ws.c_emb), p(ws.c_sh), st), 'dp_center_step')
-        self._conv(cv['final'], ws, ws.c_emb, None, h4, b.lig_arange, None, None, None, None, b.n_lig, h4, None, ws.c_sh, 9,
-                   b.lig_ptr, ws.gpred, None, 0, 0, b.B, st, 'final')
+        if self.use_fused and cv['final'].w2img112 is not None and b.tiles_final is not None:
+            self._conv(cv['final'], ws, ws.c_emb, None, h4, b.lig_arange, h4, b.lig_arange, None, None, b.n_lig, h4, None, ws.c_sh, 9,
+                       b.lig_ptr, ws.gpred, None, 0, 0, b.B, st, 'final', b.tiles_final)
+        else:
+            self._conv(cv['final'], ws, ws.c_emb, None, h4, b.lig_arange, None, None, None, None, b.n_lig, h4, None, ws.c_sh, 9,
+                       b.lig_ptr, ws.gpred, None, 0, 0, b.B, st, 'final')
         L.check(lib.dp_score_head(p(ws.gpred), b.B, sw, scp, p(ws.tr), p(ws.rot), st), 'dp_score_head')
         ws.n_launches += 2
         if b.n_rot > 0:

@@ -413,7 +413,7 @@ def test_edge_mlp_tensor_core_path_matches_ffma_path(built_lib, W, E):
 # ---------------------------------------------------------------------------------------------------------------
 # dp_conv_fused at kernel level (through the C ABI)
 # ---------------------------------------------------------------------------------------------------------------
-_CF = {0: (20, 50, 600, 9), 1: (50, 80, 1100, 9), 2: (80, 100, 1600, 9), 3: (100, 100, 2200, 9), 5: (100, 40, 1600, 8)}
+_CF = {0: (20, 50, 600, 9), 1: (50, 80, 1100, 9), 2: (80, 100, 1600, 9), 3: (100, 100, 2200, 9), 4: (100, 12, 200, 9), 5: (100, 40, 1600, 8)}
 
 
 def _conv_case(layer, degs, seed=0, shift=0, n_in=700):
@@ -467,6 +467,8 @@ def _conv_reference(layer, t):
     if layer == 5:
         sh_ir, _ = e3.full_tp_irreps_out(e3.sh_irreps(2), [(1, 2, 1)])
         in_ir, out_ir = seq[3], e3.parse_irreps('20x0o + 20x0e')
+    elif layer == 4:                                    # final_conv
+        in_ir, sh_ir, out_ir = seq[3], e3.sh_irreps(2), e3.parse_irreps('2x1o + 2x1e')
     else:
         in_ir, sh_ir, out_ir = seq[min(layer, 3)], e3.sh_irreps(2), seq[min(layer + 1, 3)]
     instrs, numel = e3.fctp_instructions(in_ir, sh_ir, out_ir)
@@ -522,6 +524,25 @@ def test_conv_fused_matches_float64_reference(built_lib, layer):
     ref = _conv_reference(layer, t)
     got = _run_conv_fused(layer, t, built_lib).double()
     assert rel(got, ref) < 2e-6, rel(got, ref)
+
+
+def test_conv_fused_final_conv_matches_float64_reference(built_lib):
+    """final_conv (fc 40 -> 40 -> 200, outputs 2x1o + 2x1e) on the fused kernel: both MLP layers zero padded to 60 / 60, the
+    third attribute block re-reads part B against zero weights (engine.ConvWeights).  Degrees like the centre graph's (one edge
+    per atom) plus the tile-boundary cases."""
+    rng = np.random.default_rng(4)
+    degs = np.concatenate([rng.integers(20, 60, 150), [128, 0, 1, 127, 3, 256, 100, 79, 79, 79, 200, 5]])
+    t = _conv_case(4, degs, seed=4)
+    t['ic'] = t['ib'].clone()
+    t['w1'][40:, :] = 0; t['w1'][:, 40:] = 0; t['b1'][40:] = 0; t['w3'][:, 40:] = 0
+    t['oscale'], t['oshift'] = torch.ones(12), torch.zeros(12)
+    ref = _conv_reference(4, t)
+    got = _run_conv_fused(4, t, built_lib, flat=True, trim=True).double()
+    assert rel(got, ref) < 2e-6, rel(got, ref)
+    # the same through the unfused pipeline's contraction kernel (what final_conv ran on before): same sums up to rounding
+    t2 = dict(t)
+    got2 = _run_conv_fused(4, t2, built_lib, flat=True, trim=True, mode=2, out0=got.float())
+    assert rel(got2.double(), 2 * ref) < 2e-6
 
 
 @pytest.mark.parametrize('layer', [0, 3])
