@@ -217,32 +217,33 @@ HOST_PACK_MAX_GRAPHS = 64    # batches of up to this many (pair, sample) graphs 
 
 
 def grouped_tiles(deg, nodes_per_graph, group=TILE_GROUP, cap=TILE_EDGES):
-    """greedy_tiles restarted at every group of `group` consecutive graphs instead of at every graph, for ALL groups at once
-    (numpy, vectorised across groups; the walk over a group's nodes stays sequential like tile_walk in conv_fused.cuh).
+    """greedy_tiles restarted at every group of `group` consecutive graphs instead of at every graph, for ALL groups at once.
+    Like tile_walk in conv_fused.cuh: the tile that starts at node i ends before nxt(i) = the first j > i with
+    seg[j + 1] - seg[i] > cap or j - i == cap (one vectorised searchsorted over all nodes), then every group hops from tile
+    start to tile start (numpy, vectorised across groups: as many steps as the longest group has tiles).
     deg: edge count of every node of the expanded batch, nodes_per_graph: [B].  Returns the first node of every tile
     (global node indices, int64) or None if a node exceeds the cap."""
     deg = np.asarray(deg, dtype=np.int64)
     if deg.size and int(deg.max()) > cap:
         return None
-    gstart = np.concatenate([[0], np.cumsum(nodes_per_graph)])[::group]
-    gend = np.append(gstart[1:], int(np.sum(nodes_per_graph)))
-    size = gend - gstart
-    M = int(size.max()) if size.size else 0
-    D = np.zeros((len(gstart), M), dtype=np.int64)
-    valid = np.arange(M)[None, :] < size[:, None]
-    D[valid] = deg
-    first = np.zeros_like(valid)
-    fill = np.zeros(len(gstart), dtype=np.int64)
-    nodes = np.zeros(len(gstart), dtype=np.int64)
-    opened = np.zeros(len(gstart), dtype=bool)
-    for j in range(M):
-        new = valid[:, j] & (~opened | (fill + D[:, j] > cap) | (nodes == cap))
-        first[:, j] = new
-        fill = np.where(new, 0, fill) + D[:, j]
-        nodes = np.where(new, 0, nodes) + 1
-        opened |= new
-    gi, ji = np.nonzero(first)
-    return gstart[gi] + ji
+    n = int(deg.size)
+    gstart = np.concatenate([[0], np.cumsum(nodes_per_graph)])[::group].astype(np.int64)
+    gend = np.append(gstart[1:], int(np.sum(nodes_per_graph))).astype(np.int64)
+    if gstart.size and gstart[-1] >= n and gend[-1] <= gstart[-1]:
+        gstart, gend = gstart[:-1], gend[:-1]                               # (a trailing empty group)
+    seg = np.concatenate([[0], np.cumsum(deg)])
+    idx = np.arange(n, dtype=np.int64)
+    gid = np.searchsorted(gstart, idx, side='right') - 1
+    j = np.searchsorted(seg, seg[:-1] + cap, side='right') - 1             # largest j with seg[j] - seg[i] <= cap
+    nxt = np.maximum(idx + 1, np.minimum(np.minimum(j, idx + cap), gend[gid] if n else idx))
+    out, cur = [], gstart[gstart < gend]
+    end = gend[gstart < gend]
+    while cur.size:
+        out.append(cur)
+        step = nxt[cur]
+        keep = step < end
+        cur, end = step[keep], end[keep]
+    return np.sort(np.concatenate(out)) if out else np.zeros(0, np.int64)
 
 
 def greedy_tiles(deg, cap=TILE_EDGES):
