@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdiffphore_sm100.so')
+# DIFFPHORE_LIB: another build of the same library (A/B runs of kernel variants on one box); default: the in-tree build
+LIB_PATH = os.environ.get('DIFFPHORE_LIB') or os.path.join(_HERE, 'libdiffphore_sm100.so')
 
 c_fp = C.c_void_p       # device pointers travel as integers
 i32 = C.c_int32
