@@ -429,6 +429,15 @@ def _pair_arrays(g):
         pp_src=pe[0][po].astype(np.int32), pp_dst=pe[1][po].astype(np.int32), pp_ptr=pp_ptr)
 
 
+def expand_mask_rows_host(pa, S):
+    """mask_rotate rows of the expanded batch (pair-major: the S samples of a pair carry the pair's rows) and the byte offset of
+    every graph's rows, built on the host with S copies per pair; equal to the generic Level expansion (tested)."""
+    m_g = np.repeat(np.asarray([len(q.rot_u) * q.n for q in pa], dtype=np.int64), S)
+    mask = np.concatenate([np.tile(np.asarray(q.mask).reshape(-1).astype(np.uint8), S) for q in pa])
+    off = np.concatenate([np.zeros(1, np.int64), np.cumsum(m_g)[:-1]])
+    return torch.from_numpy(mask), torch.from_numpy(off)
+
+
 class PackedBatch:
     """Flattened device arrays for B graphs (PyG-Batch-like; graph g = pair g // samples, sample g % samples).
 
@@ -561,10 +570,15 @@ class PackedBatch:
         tn = grouped_tiles(np.repeat(n_p, S), np.ones(B, np.int64), group=64)
         self.tiles_final = None if tn is None else (i32(torch.cat([up(tn), torch.full((1,), B, **i64)])), None, len(tn))
         # ---- mask_rotate rows (uint8) and their per-graph byte offsets
-        msk = Level(nrot_p * n_p)
-        self.mask = up(np.concatenate([q.mask.reshape(-1) for q in pa]).astype(np.uint8))[msk.src].contiguous() \
-            if msk.total else torch.zeros(0, dtype=torch.uint8, device=device)
-        self.mask_off = msk.gbase[:-1].contiguous()
+        if on_host:
+            # (the largest expansion of a small job - n_rot x n_atoms bytes per graph: the S copies of a pair's rows are S memcpys
+            # here instead of three int64 index arrays of that size and a gather; same layout)
+            self.mask, self.mask_off = expand_mask_rows_host(pa, S)
+        else:
+            msk = Level(nrot_p * n_p)
+            self.mask = up(np.concatenate([q.mask.reshape(-1) for q in pa]).astype(np.uint8))[msk.src].contiguous() \
+                if msk.total else torch.zeros(0, dtype=torch.uint8, device=device)
+            self.mask_off = msk.gbase[:-1].contiguous()
         self.lig_arange = torch.arange(self.n_lig, dtype=torch.int32, device=device)
         # ---- node-level features
         f32c = lambda key: up(np.concatenate([getattr(q, key) for q in pa], 0).astype(np.float32))

@@ -241,6 +241,23 @@ def test_packed_batch_expands_samples_like_a_naive_replication():
     assert a.tiles_cross_lig[2] > 0 and a.tiles_cross_lig[0].shape[0] == a.tiles_cross_lig[2] + 1
 
 
+def test_host_mask_expansion_equals_the_generic_level_expansion():
+    """Host-packed batches build the expanded mask_rotate rows with S copies per pair (engine.expand_mask_rows_host); the result
+    must equal the generic index expansion (pairs with and without rotatable bonds, several samples)."""
+    from diffphore_b200.engine import ModelWeights, PackedBatch, expand_mask_rows_host, _pair_arrays
+    graphs = load_pairs('synthetic', 3, 12, 5) + load_pairs('synthetic', 1, 3, 4) + load_pairs('synthetic', 2, 20, 6)
+    w = ModelWeights(random_state_dict(0), 'cpu')
+    for S in (1, 4):
+        a = PackedBatch(graphs, S, w, 'cpu')
+        mask, off = expand_mask_rows_host([_pair_arrays(g) for g in graphs], S)
+        assert mask.dtype == a.mask.dtype and torch.equal(mask, a.mask)
+        assert off.dtype == a.mask_off.dtype and torch.equal(off, a.mask_off)
+    g0 = load_pairs('synthetic', 1, 3, 4)                                         # no rotatable bond anywhere
+    a = PackedBatch(g0, 2, w, 'cpu')
+    mask, off = expand_mask_rows_host([_pair_arrays(g) for g in g0], 2)
+    assert mask.numel() == a.mask.numel() == 0 and torch.equal(off, a.mask_off)
+
+
 @pytest.mark.parametrize('layout', ['paths', 'flat', 'flat_trim', 'gen2'])
 def test_engine_conv_dispatch_follows_the_weight_layout(monkeypatch, layout):
     """Host glue of Engine._conv (no GPU: the library object is replaced by a recorder): DIFFPHORE_W2=paths calls dp_conv_fused with
